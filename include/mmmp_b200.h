@@ -1,0 +1,330 @@
+/*
+ * mmmp_b200.h — C ABI of the B200-native PRM roadmap-construction hot path.
+ *
+ * This is the drop-in boundary for ViktorLaurens/MMMP's learning phase
+ * (sample -> FK -> config/edge collision -> neighbour search -> adjacency).
+ * The reference is pure Python calling pybullet / scipy; every entry point
+ * below names the reference call site (path:line under the reference tree)
+ * whose arithmetic it replaces.  A maintainer binds it with ctypes
+ * (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary;
+ *   - `*_d` pointers are DEVICE memory, `*_h` pointers are HOST memory;
+ *   - every device entry point is asynchronous on `stream` (a cudaStream_t
+ *     passed as void*, NULL = legacy default stream); the caller owns and
+ *     allocates every output buffer; nothing is retained after return;
+ *   - return value: 0 = MMMP_OK, 1..99 = argument error, 1000+e = cudaError e;
+ *   - configurations are row-major [N, ld] with ld >= D; the fp32 copies used
+ *     by the spatial kernels are padded to ld % 4 == 0 for 16-byte loads.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns 1000 + cudaErrorNoDevice (or whatever CUDA reports).
+ */
+#ifndef MMMP_B200_H
+#define MMMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMMP_OK 0
+#define MMMP_ERR_ARG 1
+#define MMMP_ERR_LIMIT 2
+#define MMMP_ERR_KIND 3
+#define MMMP_ERR_CUDA_BASE 1000
+
+#define MMMP_MAX_JOINTS 8     /* joints per serial chain                       */
+#define MMMP_MAX_SPHERES 320  /* collision spheres per robot                   */
+#define MMMP_MAX_PAIR_TABLES 2 /* exact 2-joint link-pair tables per robot       */
+#define MMMP_PAIR_TABLE_WORDS 4096 /* 32-bit words per table (<= 131072 cells)  */
+#define MMMP_MAX_LINKS 16     /* collision link ids per robot                  */
+#define MMMP_MAX_ROBOTS 16    /* robots per world                              */
+#define MMMP_MAX_OBSTACLES 64 /* obstacle primitives per world                 */
+#define MMMP_MAX_K 64         /* neighbours per query (k1 <= 55 in reference)  */
+#define MMMP_MAX_GROUPS 8     /* frame groups of the FK metric                 */
+
+/* ---- world description (host side, copied to the device by *_create) ---- */
+
+/* Serial chain with revolute-z joints: frame 0 = base link, frame f (1..n) =
+ * base * prod_{j<f} origin[j] * Rz(q_j); the tip frame is frame n * origin[n].
+ * Replaces: Panda.dh_params / modified_homogeneous_transform
+ * (robots/panda.py:31-40,111-122), the URDF joint origins pybullet loads
+ * (robots/robot.py:22; models/kuka_iiwa/urdf/iiwa14_spheres_collision.urdf)
+ * and Robot.base_position/base_orientation (robots/robot.py:11-12).        */
+/* Optional exact decision table for one self-collision link pair whose relative
+ * pose depends on exactly two joints (u, v): cell (iu, iv) of a regular grid over
+ * [lo_u,hi_u] x [lo_v,hi_v] holds 1 when the two link HULLS may touch anywhere in
+ * the cell (fitted offline, conservative by the cell's Lipschitz bound).  The pair
+ * is then decided by one bit lookup instead of sphere tests (Panda link5/link7,
+ * whose hulls are never more than 4 cm apart).                                  */
+typedef struct mmmp_pair_table {
+    int32_t link_a, link_b;
+    int32_t joint_u, joint_v;
+    int32_t n_u, n_v;
+    double lo_u, hi_u, lo_v, hi_v;
+    uint32_t bits[MMMP_PAIR_TABLE_WORDS];     /* bit iu * n_v + iv                      */
+} mmmp_pair_table;
+
+typedef struct mmmp_robot_desc {
+    int32_t n_joints;
+    int32_t n_spheres;
+    int32_t n_links;
+    int32_t dof_offset;                       /* column of joint 0 in a composite row */
+    int32_t n_pair_tables;
+    int32_t reserved;
+    double base[12];                          /* row-major 3x4 world_T_base            */
+    double origin[MMMP_MAX_JOINTS + 1][12];   /* row-major 3x4, see above              */
+    double sphere[MMMP_MAX_SPHERES][4];       /* x, y, z (frame local), radius         */
+    int32_t sphere_link[MMMP_MAX_SPHERES];    /* collision link id, < n_links; sorted  */
+    int32_t link_frame[MMMP_MAX_LINKS];       /* frame of link l: 0 = base, f = after joint f-1 */
+    uint32_t self_mask[MMMP_MAX_LINKS];       /* bit b of [a]: test link a vs link b   */
+    mmmp_pair_table pair_table[MMMP_MAX_PAIR_TABLES];
+} mmmp_robot_desc;
+
+enum { MMMP_OBS_PLANE = 0, MMMP_OBS_SPHERE = 1, MMMP_OBS_BOX = 2, MMMP_OBS_CYLINDER = 3 };
+
+/* PLANE   : p = {nx,ny,nz,d}: solid half-space n.x <= d (unit n)
+ * SPHERE  : p = {cx,cy,cz,r}
+ * BOX     : p = {cx,cy,cz, hx,hy,hz, R row-major 3x3 (world_R_box)}
+ * CYLINDER: p = {cx,cy,cz, ax,ay,az (unit axis), half_len, radius}
+ * Replaces the pybullet bodies passed as `obstacles` to
+ * Environment(agents, obstacles) (planners/prm/pybullet/env.py:16-19).    */
+typedef struct mmmp_obstacle_desc {
+    int32_t type;
+    int32_t body;      /* obstacle body id (several primitives may share one) */
+    double p[16];
+} mmmp_obstacle_desc;
+
+/* Planar world: replaces planners/prm/planar/env.py:21-47 (map bounds, arms,
+ * Rectangle/Circle obstacles) and robots/planar_arm.py:12-21.              */
+enum { MMMP_POBS_RECT = 0, MMMP_POBS_CIRCLE = 1 };
+typedef struct mmmp_planar_desc {
+    int32_t n_arms;
+    int32_t n_obstacles;
+    int32_t n_links[MMMP_MAX_ROBOTS];
+    int32_t dof_offset[MMMP_MAX_ROBOTS];
+    double link_len[MMMP_MAX_ROBOTS][MMMP_MAX_JOINTS];
+    double base[MMMP_MAX_ROBOTS][2];
+    double bounds[4];                          /* xmin, xmax, ymin, ymax            */
+    int32_t obs_type[MMMP_MAX_OBSTACLES];
+    double obs[MMMP_MAX_OBSTACLES][4];         /* RECT x,y,w,h ; CIRCLE cx,cy,r,-   */
+    double joint_link_radius;                  /* 0.5 in planar/env.py:130          */
+} mmmp_planar_desc;
+
+typedef struct mmmp_world mmmp_world;          /* opaque; owns its device tables    */
+
+int mmmp_world_create(const mmmp_robot_desc* robots_h, int n_robots,
+                      const mmmp_obstacle_desc* obstacles_h, int n_obstacles,
+                      mmmp_world** out);
+int mmmp_planar_world_create(const mmmp_planar_desc* desc_h, mmmp_world** out);
+int mmmp_world_destroy(mmmp_world* w);
+/* total joint count of the composite configuration (sum over robots) */
+int mmmp_world_dof(const mmmp_world* w);
+
+/* ---- collision flags: which predicate families a check includes --------- */
+enum {
+    MMMP_CHECK_SELF = 1,        /* env.py:77-84 / planar env.py:208-217              */
+    MMMP_CHECK_OBSTACLES = 2,   /* env.py:51-68 / planar env.py:148-205              */
+    MMMP_CHECK_ROBOTS = 4,      /* env.py:70-75 / planar env.py:78-117               */
+    MMMP_CHECK_BOUNDS = 8       /* planar env.py:220-229 (ignored by spatial worlds) */
+};
+
+/* ---- (a) joint-space sampling -------------------------------------------
+ * np.random.uniform(lo, hi) then np.round(.,2):
+ * planners/prm/pybullet/decoupled/decoupled_prm.py:310-318,
+ * planners/prm/pybullet/coupled/coupled_prm.py:88-94,
+ * planners/prm/planar/single_arm/prm.py:52-58.
+ * Counter-based Philox4x32-10: sample i, joint j depends only on
+ * (seed, first_index + i, j).  round_dp < 0 disables rounding.
+ * out64_d [N, ld64] (may be NULL), out32_d [N, ld32] (may be NULL; padding
+ * columns are zero-filled).                                                */
+int mmmp_sample_uniform(const double* lo_h, const double* hi_h, int D,
+                        int64_t N, uint64_t seed, uint64_t first_index, int round_dp,
+                        double* out64_d, int ld64, float* out32_d, int ld32,
+                        void* stream);
+
+/* fp64 [N, ld64] -> zero-padded fp32 [N, ld32] */
+int mmmp_pack_f32(const double* q64_d, int ld64, int D, int64_t N,
+                  float* out32_d, int ld32, void* stream);
+
+/* ---- (b) forward kinematics ---------------------------------------------
+ * Panda.positions_from_fk (robots/panda.py:151-173): out_pos_d
+ * [N, n_joints+1, 3] = origins of frames 1..n and of the tip, fp32.
+ * out_T_d (may be NULL) [N, n_joints+1, 12] row-major 3x4 frame poses
+ * (Panda.forward_kinematics robots/panda.py:124-144 = last frame).         */
+int mmmp_fk_chain(const mmmp_world* w, int robot, const float* q_d, int ld, int64_t N,
+                  float* out_pos_d, float* out_T_d, void* stream);
+/* feature rows of the FK metric: out_d [N, ldf] fp32 = xyz of the selected
+ * frames (frames_h[g] in 1..n_joints+1, the tip being n_joints+1), zero padded.
+ * Panda.task_space_pose_distance (robots/panda.py:248-254) only depends on
+ * frames 3,4,5(=6),7,8 -> 5 groups with weights 1,1,2,1,1.                  */
+int mmmp_fk_features(const mmmp_world* w, int robot, const float* q_d, int ld, int64_t N,
+                     const int32_t* frames_h, int n_frames, float* out_d, int ldf,
+                     void* stream);
+/* frame groups of the FK metric for mmmp_fk_features / mmmp_metric: frames whose
+ * origin depends on q, coincident consecutive frames merged with multiplicity as
+ * weight.  frames_h / weights_h hold MMMP_MAX_GROUPS entries.                 */
+int mmmp_fk_metric_groups(const mmmp_world* w, int robot, int32_t* frames_h,
+                          float* weights_h, int* n_groups_h);
+/* same chain in fp64 (used to re-rank k-NN candidates; 1e-15 parity)       */
+int mmmp_fk_chain_f64(const mmmp_world* w, int robot, const double* q_d, int ld, int64_t N,
+                      double* out_pos_d, void* stream);
+/* PlanarArm.forward_kinematics (robots/planar_arm.py:23-40), fp64:
+ * out_pos_d [N, n_links, 2]                                                 */
+int mmmp_planar_fk(const mmmp_world* w, int arm, const double* q_d, int ld, int64_t N,
+                   double* out_pos_d, void* stream);
+
+/* ---- (c) collision checks -----------------------------------------------
+ * Spatial worlds: sphere decomposition of every link against obstacle
+ * primitives, the robot's own non-adjacent links and other robots' links;
+ * replaces pybullet getClosestPoints(distance=0) at
+ * planners/prm/pybullet/env.py:65,72,81 as composed by
+ * DecoupledPRM.is_collision_free_sample (decoupled_prm.py:840-850) and
+ * CoupledPRM.is_collision_free_sample (coupled/coupled_prm.py:143-160).
+ * Planar worlds: the analytic fp64 predicates of planners/prm/planar/env.py.
+ * robot >= 0: q rows hold that robot's joints only (decoupled planners);
+ * robot  < 0: q rows are composite rows (all robots; coupled planners).
+ * out_d[i] = 1 if configuration i is IN COLLISION, else 0.                 */
+int mmmp_collide_configs(const mmmp_world* w, int robot, const void* q_d, int ld,
+                         int64_t N, uint32_t flags, uint8_t* out_d, void* stream);
+
+/* is_collision_free_edge (decoupled_prm.py:855-863, coupled_prm.py:179-187,
+ * planar single_arm/prm.py:161-169): for t = i*step, i in [0, n_steps):
+ * q = qa + t (qb - qa); out_d[e] = 1 if ANY interpolant collides.
+ * edges_d [E,2] int32 rows (a, b) index q_d; one warp per edge, lanes are
+ * interpolation steps, warp-ballot early exit.                             */
+int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
+                       const int32_t* edges_d, int64_t E, int n_steps, double step,
+                       uint32_t flags, uint8_t* out_d, void* stream);
+/* same, with explicit endpoint arrays qa_d[e], qb_d[e] (start/goal hookup,
+ * decoupled_prm.py:943-995; query-phase pair lists)                         */
+int mmmp_collide_segments(const mmmp_world* w, int robot, const void* qa_d, const void* qb_d,
+                          int ld, int64_t E, int n_steps, double step,
+                          uint32_t flags, uint8_t* out_d, void* stream);
+/* robot_robot_collision(q1, q2, r1, r2) on a pair list
+ * (decoupled_prm.py:871-876; cbsprm.py:165-183): qa_d rows are robot ra's
+ * joints, qb_d rows robot rb's.                                            */
+int mmmp_collide_robot_pairs(const mmmp_world* w, int ra, int rb, const void* qa_d,
+                             const void* qb_d, int ld, int64_t N, uint8_t* out_d,
+                             void* stream);
+
+/* stable compaction of the rows with flag == 0 (rejection sampling):
+ * idx_out_d [<=N] ascending row indices; count_d receives the count.        */
+int mmmp_compact_free(const uint8_t* flags_d, int64_t N, int32_t* idx_out_d,
+                      int32_t* count_d, void* stream);
+/* out[i, :] = in[idx[i], :] for i < n ; row_bytes a multiple of 4             */
+int mmmp_gather_rows(const void* in_d, int row_bytes, const int32_t* idx_d, int64_t n,
+                     void* out_d, void* stream);
+
+/* ---- (d) neighbour search ----------------------------------------------- */
+enum {
+    MMMP_METRIC_L2 = 0,            /* np.linalg.norm(q1-q2): decoupled_prm.py:824, coupled_prm.py:131 */
+    MMMP_METRIC_GROUP_L2_SUM = 1,  /* sum_g w_g ||p_g(q1)-p_g(q2)||: robots/panda.py:248-254          */
+    MMMP_METRIC_SQ_SUM = 2         /* sum ||.||^2: robots/planar_arm.py:54-61                          */
+};
+
+/* metric description: features are fp32 rows [N, ldf]; for GROUP_L2_SUM the
+ * first 3*n_groups columns are xyz triples with weights w[g].               */
+typedef struct mmmp_metric {
+    int32_t kind;
+    int32_t dim;                      /* feature columns used                       */
+    int32_t n_groups;
+    float weight[MMMP_MAX_GROUPS];
+} mmmp_metric;
+
+/* Brute-force k nearest neighbours: replaces the heap loops
+ * decoupled_prm.py:480-504,527-550,943-995 and KDTree.query at
+ * coupled/degree_coupled_prm.py:67, planar single_arm/degree_prm.py:178.
+ * For query row i (global id query_id0 + i) the k nearest reference rows with
+ * id in [id_lo, id_hi_i) excluding the query's own id when exclude_self;
+ * id_hi_i = min(n_ref, causal ? query id : n_ref)  (causal = only earlier
+ * nodes, the incremental planners).  Output ascending (dist, id); missing
+ * slots get id -1 and dist +inf.  out_dist_d may be NULL.                   */
+int mmmp_knn(const float* ref_d, int64_t n_ref, const float* query_d, int64_t n_query,
+             int ldf, const mmmp_metric* metric_h, int k, int exclude_self, int causal,
+             int64_t query_id0, int32_t* out_idx_d, float* out_dist_d, void* stream);
+
+/* Re-rank candidates in fp64 with the reference's own arithmetic order:
+ * cand_idx_d [n_query, kc] (from mmmp_knn with kc >= k) -> out [n_query, k]
+ * ascending (dist64, id).  L2/SQ_SUM: rows of ref64_d/query64_d [., ld64]
+ * are the configurations (or fp64 features); GROUP_L2_SUM: they are fp64
+ * frame positions [., ld64] from mmmp_fk_chain_f64 and metric->dim selects
+ * the triples.  ambiguous_d (may be NULL) [n_query] = 1 when the fp32 scan
+ * could not separate rank k from rank kc (distance gap < tie_eps).          */
+int mmmp_knn_refine(const double* ref64_d, const double* query64_d, int ld64,
+                    const mmmp_metric* metric_h, const int32_t* cand_idx_d,
+                    const float* cand_dist_d, int64_t n_query, int kc, int k,
+                    double tie_eps, int32_t* out_idx_d, double* out_dist_d,
+                    uint8_t* ambiguous_d, void* stream);
+
+/* Radius search (dist <= r, or dist < r when strict): replaces
+ * connect_nearest_neighbors_distance (decoupled_prm.py:553-571),
+ * DistancePRM.add_n_samples (planar single_arm/distance_prm.py:40-52,
+ * coupled/distance_coupled_prm.py:40-52) and KDTree.query_ball_point
+ * (coupled/distance_coupled_prm.py:133).  The fp32 rows drive a conservative
+ * filter; rows that pass are decided in fp64 on ref64_d/query64_d with the
+ * reference's arithmetic (metric64_h describes those rows: L2 -> configs,
+ * GROUP_L2_SUM / SQ_SUM -> fp64 frame / link positions, n_groups = frames),
+ * so membership is exact.  Two-pass CSR: call with out_idx_d == NULL to fill
+ * counts_d [n_query]; exclusive-scan them into offsets_d [n_query+1]
+ * (mmmp_exclusive_scan_i32), then call again to fill out_idx_d / out_dist_d
+ * (ids ascending within a row).                                             */
+int mmmp_radius(const float* ref_d, const double* ref64_d, int64_t n_ref,
+                const float* query_d, const double* query64_d, int64_t n_query,
+                int ldf, int ld64, const mmmp_metric* metric_h,
+                const mmmp_metric* metric64_h, double r, int strict, int exclude_self,
+                int exclude_zero, int causal, int64_t query_id0, int32_t* counts_d,
+                const int64_t* offsets_d, int32_t* out_idx_d, double* out_dist_d,
+                void* stream);
+int mmmp_exclusive_scan_i32(const int32_t* in_d, int64_t n, int64_t* out_d /* n+1 */,
+                            void* stream);
+
+/* ---- host-buffer entry points (the reference-facing call) ----------------
+ * One call = the learning phase of a decoupled degree PRM for one robot on
+ * caller-provided samples, host memory in, host memory out
+ * (DecoupledPRM.generate_roadmap decoupled_prm.py:231-260 with the joint-space
+ * sampler's accept test decoupled_prm.py:310-321):
+ *   H2D samples -> config collision -> compaction of the free samples (= the
+ *   nodes, ids in input order) -> metric features -> k-NN scan + fp64 re-rank
+ *   -> edge collision of every (node, candidate) pair -> D2H.
+ * q64_h [N, D] fp64.  Outputs (host, sized for N rows; the first *n_nodes_h
+ * rows are valid): node_src_h [N] input row of node i, nbr_idx_h [N, k] int32
+ * node ids ascending (dist, id) (-1 = none), nbr_dist_h [N, k] fp64 (may be
+ * NULL), edge_free_h [N, k] u8 (1 = the straight edge is collision free).
+ * metric_kind: MMMP_METRIC_L2 or MMMP_METRIC_GROUP_L2_SUM (Panda FK metric,
+ * all chain frames, panda.py:248-254).  Synchronous.  timings_ms_h (may be
+ * NULL) [8]: h2d, config collision+compaction, features, knn scan, re-rank,
+ * edge collision, d2h, total (CUDA events).                                 */
+int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, const double* q64_h,
+                                 int64_t N, int D, int metric_kind, int k, int n_steps,
+                                 double step, uint32_t flags, int64_t* n_nodes_h,
+                                 int32_t* node_src_h, int32_t* nbr_idx_h,
+                                 double* nbr_dist_h, uint8_t* edge_free_h,
+                                 float* timings_ms_h);
+
+/* edges_d[e] = (e / k, nbr_d[e]) for a flat [n, k] neighbour table            */
+int mmmp_edges_from_knn(const int32_t* nbr_d, int64_t n, int k, int32_t* edges_d,
+                        void* stream);
+
+/* Greedy sequential accept pass of connect_nearest_neighbors_degree
+ * (decoupled_prm.py:496-503) on precomputed candidates, host side, native:
+ * nodes in id order, candidates in (dist,id) order, accept while deg < k2 on
+ * both ends, edge free and not already present.  adj_h [N, cap] int32 (-1
+ * padded), deg_h [N].  cap_other_end = 0 reproduces connect_extra_nodes_*.  */
+int mmmp_greedy_degree_connect(const int32_t* nbr_idx_h, const uint8_t* edge_free_h,
+                               int64_t N, int k1, int k2, int cap, int32_t* adj_h,
+                               int32_t* deg_h);
+
+/* library / device introspection */
+int mmmp_version(void);
+int mmmp_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+/* number of kernel launches issued by this library since load (bench.py's
+ * gpu_launches)                                                             */
+int64_t mmmp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMMP_B200_H */

@@ -1,0 +1,524 @@
+"""Thin Python layer over the C ABI: worlds (device tables) and batched kernels.
+
+torch is used only as plumbing (device buffers, the current CUDA stream); every
+computation is a call into libmmmp_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (CHECK_BOUNDS, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_SELF, METRIC_GROUP_L2_SUM, METRIC_L2,
+                   METRIC_SQ_SUM, Metric, MmmpError)
+
+GEOMETRY_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "geometry")
+
+
+# ----------------------------------------------------------------- geometry
+def load_model(name: str) -> dict:
+    with open(os.path.join(GEOMETRY_DIR, name + ".json")) as f:
+        return json.load(f)
+
+
+def quat_to_matrix(q) -> np.ndarray:
+    """xyzw quaternion -> 3x3 (what scipy Rotation.from_quat(q).as_matrix() returns,
+    reference robots/panda.py:127)."""
+    x, y, z, w = (float(v) for v in q)
+    n = np.sqrt(x * x + y * y + z * z + w * w)
+    x, y, z, w = x / n, y / n, z / n, w / n
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)],
+    ])
+
+
+def base_matrix(position=(0, 0, 0), orientation=(0, 0, 0, 1)) -> np.ndarray:
+    T = np.eye(4)
+    T[:3, :3] = quat_to_matrix(orientation)
+    T[:3, 3] = np.asarray(position, dtype=np.float64)
+    return T
+
+
+def mdh_origin(a: float, d: float, alpha: float) -> np.ndarray:
+    """Fixed part of the modified-DH transform (theta = 0) of robots/panda.py:111-122:
+    T_i(theta) = origin * Rz(theta)."""
+    ca, sa = np.cos(alpha), np.sin(alpha)
+    return np.array([[1.0, 0.0, 0.0, a], [0.0, ca, -sa, -sa * d], [0.0, sa, ca, ca * d], [0, 0, 0, 1.0]])
+
+
+def rpy_origin(xyz, rpy) -> np.ndarray:
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = Rz @ Ry @ Rx
+    T[:3, 3] = xyz
+    return T
+
+
+def model_origins(model: dict) -> list:
+    if "dh_modified" in model:
+        return [mdh_origin(r["a"], r["d"], r["alpha"]) for r in model["dh_modified"]]
+    org = [rpy_origin(j["xyz"], j["rpy"]) for j in model["joint_origins"]]
+    org.append(rpy_origin(model["tip"]["xyz"], model["tip"]["rpy"]))
+    return org
+
+
+@dataclass
+class RobotSpec:
+    """One serial arm of a spatial world."""
+    model: dict
+    base: np.ndarray = field(default_factory=lambda: np.eye(4))
+    dof_offset: int = 0
+    use_pair_tables: bool = True
+
+    def desc(self) -> _lib.RobotDesc:
+        m = self.model
+        d = _lib.RobotDesc()
+        n = int(m["n_joints"])
+        d.n_joints = n
+        d.dof_offset = int(self.dof_offset)
+        for i, v in enumerate(np.asarray(self.base, dtype=np.float64)[:3, :].ravel()):
+            d.base[i] = v
+        for j, O in enumerate(model_origins(m)):
+            for i, v in enumerate(np.asarray(O, dtype=np.float64)[:3, :].ravel()):
+                d.origin[j][i] = v
+        links = m["links"]
+        d.n_links = len(links)
+        if len(links) > _lib.MAX_LINKS:
+            raise MmmpError("too many collision links")
+        sph = sorted(m["spheres"], key=lambda s: s["link_id"])
+        if len(sph) > _lib.MAX_SPHERES:
+            raise MmmpError(f"{len(sph)} spheres > {_lib.MAX_SPHERES}")
+        d.n_spheres = len(sph)
+        frames = {}
+        for k, s in enumerate(sph):
+            for i in range(3):
+                d.sphere[k][i] = s["center"][i]
+            d.sphere[k][3] = s["radius"]
+            d.sphere_link[k] = s["link_id"]
+            frames[s["link_id"]] = s["frame"]
+        for l in range(len(links)):
+            d.link_frame[l] = frames.get(l, 0)
+        for a, b in m["self_pairs"]:
+            d.self_mask[a] |= 1 << b
+        tables = m.get("pair_tables", []) if self.use_pair_tables else []
+        d.n_pair_tables = len(tables)
+        for t, pt in enumerate(tables):
+            T = d.pair_table[t]
+            for key in ("link_a", "link_b", "joint_u", "joint_v", "n_u", "n_v"):
+                setattr(T, key, int(pt[key]))
+            for key in ("lo_u", "hi_u", "lo_v", "hi_v"):
+                setattr(T, key, float(pt[key]))
+            words = np.frombuffer(bytes.fromhex(pt["words_hex"]), dtype=np.uint32)
+            C.memmove(T.bits, words.ctypes.data, words.nbytes)
+        return d
+
+
+# obstacle primitives (plain dicts so the oracle can read the same description)
+def plane(normal=(0, 0, 1), offset=0.0, body=None) -> dict:
+    n = np.asarray(normal, dtype=np.float64)
+    n = n / np.linalg.norm(n)
+    return {"type": "plane", "normal": n.tolist(), "offset": float(offset), "body": body}
+
+
+def box(center, half, R=None, body=None) -> dict:
+    R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64)
+    return {"type": "box", "center": [float(v) for v in center], "half": [float(v) for v in half],
+            "R": R.tolist(), "body": body}
+
+
+def sphere(center, radius, body=None) -> dict:
+    return {"type": "sphere", "center": [float(v) for v in center], "radius": float(radius), "body": body}
+
+
+def cylinder(center, axis, half_len, radius, body=None) -> dict:
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    return {"type": "cylinder", "center": [float(v) for v in center], "axis": a.tolist(),
+            "half_len": float(half_len), "radius": float(radius), "body": body}
+
+
+def _obstacle_desc(ob: dict, index: int) -> _lib.ObstacleDesc:
+    d = _lib.ObstacleDesc()
+    d.body = index if ob.get("body") is None else int(ob["body"])
+    t = ob["type"]
+    if t == "plane":
+        d.type = _lib.OBS_PLANE
+        vals = list(ob["normal"]) + [ob["offset"]]
+    elif t == "sphere":
+        d.type = _lib.OBS_SPHERE
+        vals = list(ob["center"]) + [ob["radius"]]
+    elif t == "box":
+        d.type = _lib.OBS_BOX
+        vals = list(ob["center"]) + list(ob["half"]) + list(np.asarray(ob["R"], dtype=np.float64).ravel())
+    elif t == "cylinder":
+        d.type = _lib.OBS_CYLINDER
+        vals = list(ob["center"]) + list(ob["axis"]) + [ob["half_len"], ob["radius"]]
+    else:
+        raise MmmpError(f"unknown obstacle type {t!r}")
+    for i, v in enumerate(vals):
+        d.p[i] = float(v)
+    return d
+
+
+# ----------------------------------------------------------------- helpers
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise MmmpError("no CUDA device: mmmp_b200 has no CPU fallback for the roadmap-construction path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dev(t: torch.Tensor, dtype) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise MmmpError(f"expected a contiguous CUDA tensor of {dtype}, got {t.dtype} on {t.device}")
+    return t
+
+
+def pad4(d: int) -> int:
+    return (d + 3) & ~3
+
+
+def to_device_f64(a) -> torch.Tensor:
+    dev = _require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+def pack_f32(q64: torch.Tensor, ld32: Optional[int] = None) -> torch.Tensor:
+    q64 = _dev(q64, torch.float64)
+    N, D = q64.shape
+    ld32 = pad4(D) if ld32 is None else ld32
+    out = torch.empty((N, ld32), dtype=torch.float32, device=q64.device)
+    _lib.call("mmmp_pack_f32", _ptr(q64), D, D, N, _ptr(out), ld32, _stream())
+    return out
+
+
+def sample_uniform(lo, hi, n: int, seed: int, first_index: int = 0, round_dp: int = 2):
+    """-> (q64 [n, D], q32 [n, pad4(D)]) device tensors."""
+    dev = _require_cuda()
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    D = lo.shape[0]
+    q64 = torch.empty((n, D), dtype=torch.float64, device=dev)
+    q32 = torch.empty((n, pad4(D)), dtype=torch.float32, device=dev)
+    _lib.call("mmmp_sample_uniform", lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), D, n,
+              C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(first_index), round_dp, _ptr(q64), D, _ptr(q32),
+              pad4(D), _stream())
+    return q64, q32
+
+
+def compact_free(flags: torch.Tensor) -> torch.Tensor:
+    """Ascending indices of the rows whose flag is 0 (collision free)."""
+    flags = _dev(flags, torch.uint8)
+    n = flags.numel()
+    idx = torch.empty((n,), dtype=torch.int32, device=flags.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=flags.device)
+    _lib.call("mmmp_compact_free", _ptr(flags), n, _ptr(idx), _ptr(cnt), _stream())
+    return idx[: int(cnt.item())]
+
+
+def gather_rows(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    idx = _dev(idx, torch.int32)
+    if not t.is_contiguous():
+        raise MmmpError("gather_rows needs a contiguous tensor")
+    row_bytes = t.shape[1] * t.element_size()
+    out = torch.empty((idx.numel(), t.shape[1]), dtype=t.dtype, device=t.device)
+    _lib.call("mmmp_gather_rows", _ptr(t), row_bytes, _ptr(idx), idx.numel(), _ptr(out), _stream())
+    return out
+
+
+def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
+    counts = _dev(counts, torch.int32)
+    out = torch.empty((counts.numel() + 1,), dtype=torch.int64, device=counts.device)
+    _lib.call("mmmp_exclusive_scan_i32", _ptr(counts), counts.numel(), _ptr(out), _stream())
+    return out
+
+
+def make_metric(kind: int, dim: int, weights: Sequence[float] = ()) -> Metric:
+    m = Metric()
+    m.kind, m.dim, m.n_groups = kind, dim, len(weights)
+    for i, w in enumerate(weights):
+        m.weight[i] = w
+    return m
+
+
+def knn(ref: torch.Tensor, query: torch.Tensor, metric: Metric, k: int, exclude_self: bool = True,
+        causal: bool = False, query_id0: int = 0):
+    """fp32 scan -> (idx [nq, k] int32, dist [nq, k] fp32), ascending (dist, id)."""
+    ref, query = _dev(ref, torch.float32), _dev(query, torch.float32)
+    nq, ldf = query.shape
+    idx = torch.empty((nq, k), dtype=torch.int32, device=ref.device)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=ref.device)
+    _lib.call("mmmp_knn", _ptr(ref), ref.shape[0], _ptr(query), nq, ldf, C.byref(metric), k, int(exclude_self),
+              int(causal), query_id0, _ptr(idx), _ptr(dist), _stream())
+    return idx, dist
+
+
+def knn_refine(ref64: torch.Tensor, query64: torch.Tensor, metric64: Metric, cand_idx: torch.Tensor,
+               cand_dist: torch.Tensor, k: int, tie_eps: float = 1e-6):
+    """fp64 re-rank -> (idx [nq, k], dist64 [nq, k], ambiguous [nq] u8)."""
+    ref64, query64 = _dev(ref64, torch.float64), _dev(query64, torch.float64)
+    nq, kc = cand_idx.shape
+    idx = torch.empty((nq, k), dtype=torch.int32, device=ref64.device)
+    dist = torch.empty((nq, k), dtype=torch.float64, device=ref64.device)
+    amb = torch.empty((nq,), dtype=torch.uint8, device=ref64.device)
+    _lib.call("mmmp_knn_refine", _ptr(ref64), _ptr(query64), ref64.shape[1], C.byref(metric64),
+              _ptr(_dev(cand_idx, torch.int32)), _ptr(_dev(cand_dist, torch.float32)), nq, kc, k,
+              C.c_double(tie_eps), _ptr(idx), _ptr(dist), _ptr(amb), _stream())
+    return idx, dist, amb
+
+
+def knn_exact(ref32, ref64, query32, query64, metric32: Metric, metric64: Metric, k: int, pad: int = 6,
+              exclude_self: bool = True, causal: bool = False, query_id0: int = 0):
+    """scan with k+pad candidates, then fp64 re-rank."""
+    kc = min(k + pad, _lib.MAX_K)
+    ci, cd = knn(ref32, query32, metric32, kc, exclude_self, causal, query_id0)
+    return knn_refine(ref64, query64, metric64, ci, cd, k)
+
+
+def radius_search(ref32, ref64, query32, query64, metric32: Metric, metric64: Metric, r: float,
+                  strict: bool = False, exclude_self: bool = True, exclude_zero: bool = False,
+                  causal: bool = False, query_id0: int = 0):
+    """CSR neighbour lists within r: (offsets [nq+1] int64, idx int32, dist fp64); ids ascending per row."""
+    ref32, query32 = _dev(ref32, torch.float32), _dev(query32, torch.float32)
+    ref64, query64 = _dev(ref64, torch.float64), _dev(query64, torch.float64)
+    nq, ldf = query32.shape
+    counts = torch.zeros((nq,), dtype=torch.int32, device=ref32.device)
+    args = lambda cnt, off, oi, od: (  # noqa: E731
+        _ptr(ref32), _ptr(ref64), ref32.shape[0], _ptr(query32), _ptr(query64), nq, ldf, ref64.shape[1],
+        C.byref(metric32), C.byref(metric64), C.c_double(r), int(strict), int(exclude_self), int(exclude_zero),
+        int(causal), query_id0, _ptr(cnt), _ptr(off), _ptr(oi), _ptr(od), _stream())
+    _lib.call("mmmp_radius", *args(counts, None, None, None))
+    offsets = exclusive_scan(counts)
+    total = int(offsets[-1].item())
+    idx = torch.empty((max(total, 1),), dtype=torch.int32, device=ref32.device)
+    dist = torch.empty((max(total, 1),), dtype=torch.float64, device=ref32.device)
+    if total > 0:
+        _lib.call("mmmp_radius", *args(None, offsets, idx, dist))
+    return offsets, idx[:total], dist[:total]
+
+
+def greedy_degree_connect(nbr_idx: np.ndarray, edge_free: np.ndarray, k2: int, cap: Optional[int] = None):
+    """Native host replay of connect_nearest_neighbors_degree (decoupled_prm.py:496-503)."""
+    nbr_idx = np.ascontiguousarray(nbr_idx, dtype=np.int32)
+    edge_free = np.ascontiguousarray(edge_free, dtype=np.uint8)
+    N, k1 = nbr_idx.shape
+    cap = k2 if cap is None else cap
+    adj = np.empty((N, cap), dtype=np.int32)
+    deg = np.empty((N,), dtype=np.int32)
+    _lib.call("mmmp_greedy_degree_connect", nbr_idx.ctypes.data_as(C.c_void_p), edge_free.ctypes.data_as(C.c_void_p),
+              N, k1, k2, cap, adj.ctypes.data_as(C.c_void_p), deg.ctypes.data_as(C.c_void_p))
+    return adj, deg
+
+
+def launch_count() -> int:
+    return int(_lib.load().mmmp_launch_count())
+
+
+# ----------------------------------------------------------------- worlds
+class _World:
+    def __init__(self):
+        self._h = C.c_void_p(0)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h:
+            raise MmmpError("world already destroyed")
+        return self._h
+
+    def close(self):
+        if self._h:
+            _lib.load().mmmp_world_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # collision ----------------------------------------------------------------
+    _qdtype = torch.float32
+
+    def collide_configs(self, q: torch.Tensor, robot: int = -1, flags: int = CHECK_SELF | CHECK_OBSTACLES):
+        q = _dev(q, self._qdtype)
+        out = torch.empty((q.shape[0],), dtype=torch.uint8, device=q.device)
+        _lib.call("mmmp_collide_configs", self.handle, robot, _ptr(q), q.shape[1], q.shape[0], flags, _ptr(out),
+                  _stream())
+        return out
+
+    def collide_edges(self, q: torch.Tensor, edges: torch.Tensor, n_steps: int, step: float, robot: int = -1,
+                      flags: int = CHECK_SELF | CHECK_OBSTACLES):
+        q = _dev(q, self._qdtype)
+        edges = _dev(edges, torch.int32)
+        E = edges.numel() // 2
+        out = torch.empty((E,), dtype=torch.uint8, device=q.device)
+        _lib.call("mmmp_collide_edges", self.handle, robot, _ptr(q), q.shape[1], _ptr(edges), E, n_steps,
+                  C.c_double(step), flags, _ptr(out), _stream())
+        return out
+
+    def collide_segments(self, qa: torch.Tensor, qb: torch.Tensor, n_steps: int, step: float, robot: int = -1,
+                         flags: int = CHECK_SELF | CHECK_OBSTACLES):
+        qa, qb = _dev(qa, self._qdtype), _dev(qb, self._qdtype)
+        out = torch.empty((qa.shape[0],), dtype=torch.uint8, device=qa.device)
+        _lib.call("mmmp_collide_segments", self.handle, robot, _ptr(qa), _ptr(qb), qa.shape[1], qa.shape[0],
+                  n_steps, C.c_double(step), flags, _ptr(out), _stream())
+        return out
+
+
+def edges_from_knn(nbr: torch.Tensor) -> torch.Tensor:
+    nbr = _dev(nbr, torch.int32)
+    n, k = nbr.shape
+    edges = torch.empty((n * k, 2), dtype=torch.int32, device=nbr.device)
+    _lib.call("mmmp_edges_from_knn", _ptr(nbr), n, k, _ptr(edges), _stream())
+    return edges
+
+
+class SpatialWorld(_World):
+    """Robots (serial chains + sphere decomposition) and obstacle primitives on the device."""
+
+    def __init__(self, robots: Sequence[RobotSpec], obstacles: Sequence[dict] = ()):
+        super().__init__()
+        _require_cuda()
+        self.robots = list(robots)
+        self.obstacles = list(obstacles)
+        rd = (_lib.RobotDesc * len(self.robots))(*[r.desc() for r in self.robots])
+        od = (_lib.ObstacleDesc * max(1, len(self.obstacles)))(*[_obstacle_desc(o, i) for i, o in
+                                                                  enumerate(self.obstacles)])
+        h = C.c_void_p(0)
+        _lib.call("mmmp_world_create", rd, len(self.robots), od, len(self.obstacles), C.byref(h))
+        self._h = h
+
+    @property
+    def dof(self) -> int:
+        return int(_lib.load().mmmp_world_dof(self.handle))
+
+    def fk(self, q32: torch.Tensor, robot: int = 0, poses: bool = False):
+        q32 = _dev(q32, torch.float32)
+        L = self.robots[robot].model["n_joints"] + 1
+        pos = torch.empty((q32.shape[0], L, 3), dtype=torch.float32, device=q32.device)
+        T = torch.empty((q32.shape[0], L, 12), dtype=torch.float32, device=q32.device) if poses else None
+        _lib.call("mmmp_fk_chain", self.handle, robot, _ptr(q32), q32.shape[1], q32.shape[0], _ptr(pos), _ptr(T),
+                  _stream())
+        return (pos, T) if poses else pos
+
+    def fk64(self, q64: torch.Tensor, robot: int = 0):
+        q64 = _dev(q64, torch.float64)
+        L = self.robots[robot].model["n_joints"] + 1
+        pos = torch.empty((q64.shape[0], L, 3), dtype=torch.float64, device=q64.device)
+        _lib.call("mmmp_fk_chain_f64", self.handle, robot, _ptr(q64), q64.shape[1], q64.shape[0], _ptr(pos),
+                  _stream())
+        return pos
+
+    def metric_groups(self, robot: int = 0):
+        frames = (C.c_int32 * _lib.MAX_GROUPS)()
+        weights = (C.c_float * _lib.MAX_GROUPS)()
+        n = C.c_int(0)
+        _lib.call("mmmp_fk_metric_groups", self.handle, robot, frames, weights, C.byref(n))
+        return list(frames[: n.value]), list(weights[: n.value])
+
+    def fk_features(self, q32: torch.Tensor, robot: int = 0):
+        """fp32 feature rows of the FK metric and the matching (metric32, metric64)."""
+        q32 = _dev(q32, torch.float32)
+        frames, weights = self.metric_groups(robot)
+        ldf = pad4(3 * len(frames))
+        out = torch.empty((q32.shape[0], ldf), dtype=torch.float32, device=q32.device)
+        fr = (C.c_int32 * len(frames))(*frames)
+        _lib.call("mmmp_fk_features", self.handle, robot, _ptr(q32), q32.shape[1], q32.shape[0], fr, len(frames),
+                  _ptr(out), ldf, _stream())
+        L = self.robots[robot].model["n_joints"] + 1
+        m32 = make_metric(METRIC_GROUP_L2_SUM, 3 * len(frames), weights)
+        m64 = make_metric(METRIC_GROUP_L2_SUM, 3 * L, [1.0] * L)
+        return out, m32, m64
+
+    def collide_robot_pairs(self, qa: torch.Tensor, qb: torch.Tensor, ra: int, rb: int):
+        qa, qb = _dev(qa, torch.float32), _dev(qb, torch.float32)
+        out = torch.empty((qa.shape[0],), dtype=torch.uint8, device=qa.device)
+        _lib.call("mmmp_collide_robot_pairs", self.handle, ra, rb, _ptr(qa), _ptr(qb), qa.shape[1], qa.shape[0],
+                  _ptr(out), _stream())
+        return out
+
+    def roadmap_candidates_host(self, q64: np.ndarray, robot: int, metric_kind: int, k: int, n_steps: int,
+                                step: float, flags: int = CHECK_SELF | CHECK_OBSTACLES):
+        """Host arrays in, host arrays out (the e2e call): see include/mmmp_b200.h."""
+        q64 = np.ascontiguousarray(q64, dtype=np.float64)
+        N, D = q64.shape
+        node_src = np.empty((N,), dtype=np.int32)
+        nbr = np.empty((N, k), dtype=np.int32)
+        dist = np.empty((N, k), dtype=np.float64)
+        free = np.empty((N, k), dtype=np.uint8)
+        n_nodes = C.c_int64(0)
+        timings = np.zeros((8,), dtype=np.float32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.call("mmmp_roadmap_candidates_host", self.handle, robot, vp(q64), N, D, metric_kind, k, n_steps,
+                  C.c_double(step), flags, C.byref(n_nodes), vp(node_src), vp(nbr), vp(dist), vp(free), vp(timings))
+        n = n_nodes.value
+        return {"n_nodes": n, "node_src": node_src[:n], "nbr_idx": nbr[:n], "nbr_dist": dist[:n],
+                "edge_free": free[:n], "timings_ms": timings}
+
+
+class PlanarWorld(_World):
+    """Planar arms, map bounds and Rectangle/Circle obstacles on the device (fp64)."""
+    _qdtype = torch.float64
+
+    def __init__(self, arms: Sequence[dict], bounds, obstacles: Sequence[dict] = (), joint_link_radius: float = 0.5):
+        """arms: [{links: [..], base: (x, y)}]; obstacles: {type: 'rect', x0,y0,x1,y1} | {type:'circle', cx,cy,r}."""
+        super().__init__()
+        _require_cuda()
+        d = _lib.PlanarDesc()
+        d.n_arms = len(arms)
+        off = 0
+        for a, arm in enumerate(arms):
+            links = [float(v) for v in arm["links"]]
+            d.n_links[a] = len(links)
+            d.dof_offset[a] = off
+            off += len(links)
+            for l, v in enumerate(links):
+                d.link_len[a][l] = v
+            d.base[a][0], d.base[a][1] = float(arm["base"][0]), float(arm["base"][1])
+        for i, v in enumerate(bounds):
+            d.bounds[i] = float(v)
+        d.n_obstacles = len(obstacles)
+        for o, ob in enumerate(obstacles):
+            if ob["type"] == "rect":
+                d.obs_type[o] = _lib.POBS_RECT
+                vals = [ob["x0"], ob["y0"], ob["x1"], ob["y1"]]
+            elif ob["type"] == "circle":
+                d.obs_type[o] = _lib.POBS_CIRCLE
+                vals = [ob["cx"], ob["cy"], ob["r"], 0.0]
+            else:
+                raise MmmpError(f"unknown planar obstacle {ob['type']!r}")
+            for i, v in enumerate(vals):
+                d.obs[o][i] = float(v)
+        d.joint_link_radius = float(joint_link_radius)
+        self.arms = list(arms)
+        h = C.c_void_p(0)
+        _lib.call("mmmp_planar_world_create", C.byref(d), C.byref(h))
+        self._h = h
+
+    def fk(self, q64: torch.Tensor, arm: int = 0):
+        q64 = _dev(q64, torch.float64)
+        n = len(self.arms[arm]["links"])
+        out = torch.empty((q64.shape[0], n, 2), dtype=torch.float64, device=q64.device)
+        _lib.call("mmmp_planar_fk", self.handle, arm, _ptr(q64), q64.shape[1], q64.shape[0], _ptr(out), _stream())
+        return out

@@ -1,0 +1,155 @@
+// Shared device/host definitions for the mmmp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/mmmp_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "mmmp_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+#define MMMP_CUDA_TRY(expr)                                            \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return MMMP_ERR_CUDA_BASE + (int)_e;    \
+    } while (0)
+
+// every kernel launch of the library goes through this so that bench.py can
+// report gpu_launches from the library's own counter
+extern std::atomic<int64_t> g_mmmp_launches;
+#define MMMP_LAUNCH(kernel, grid, block, smem, stream, ...)                        \
+    do {                                                                           \
+        kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);  \
+        g_mmmp_launches.fetch_add(1, std::memory_order_relaxed);                   \
+    } while (0)
+#define MMMP_LAUNCH_CHECK()                                                        \
+    do {                                                                           \
+        cudaError_t _e = cudaPeekAtLastError();                                    \
+        if (_e != cudaSuccess) return MMMP_ERR_CUDA_BASE + (int)_e;                \
+    } while (0)
+
+// ---------------------------------------------------------------- device world
+#define MMMP_MAX_SELF_PAIRS 120
+
+struct PairTableDev {
+    int joint_u, joint_v, n_u, n_v;
+    float lo_u, inv_du, lo_v, inv_dv;
+    int word_offset;  // into WorldDev::table_bits
+    int pad[3];
+};
+
+struct RobotDev {
+    int n_joints, n_spheres, n_links, dof_offset;
+    int n_self_pairs, n_tables, base_hits_obstacles, n_moving_links;
+    float base[12];
+    float origin[MMMP_MAX_JOINTS + 1][12];
+    float4 link_bound[MMMP_MAX_LINKS];  // bounding sphere, frame local (frame-0 links: WORLD)
+    int link_frame[MMMP_MAX_LINKS];
+    int link_sphere_begin[MMMP_MAX_LINKS + 1];
+    uchar2 self_pair[MMMP_MAX_SELF_PAIRS];
+    PairTableDev table[MMMP_MAX_PAIR_TABLES];
+    float4 sphere[MMMP_MAX_SPHERES];    // frame local xyz, r (frame-0 links: WORLD xyz)
+};
+
+struct RobotDev64 {  // fp64 chain for the re-ranking FK
+    int n_joints;
+    double base[12];
+    double origin[MMMP_MAX_JOINTS + 1][12];
+};
+
+struct ObstacleDev {
+    int type;
+    int body;
+    float p[16];
+};
+
+struct WorldDev {
+    int n_robots, n_obstacles, dof, n_table_words;
+    RobotDev robots[MMMP_MAX_ROBOTS];
+    ObstacleDev obstacles[MMMP_MAX_OBSTACLES];
+    RobotDev64 robots64[MMMP_MAX_ROBOTS];
+    unsigned int table_bits[MMMP_MAX_ROBOTS * MMMP_MAX_PAIR_TABLES * MMMP_PAIR_TABLE_WORDS / 4];
+};
+
+struct PlanarDev {
+    int n_arms, n_obstacles, dof, total_links;
+    int n_links[MMMP_MAX_ROBOTS];
+    int dof_offset[MMMP_MAX_ROBOTS];
+    int link_begin[MMMP_MAX_ROBOTS + 1];
+    double link_len[MMMP_MAX_ROBOTS][MMMP_MAX_JOINTS];
+    double base[MMMP_MAX_ROBOTS][2];
+    double bounds[4];
+    int obs_type[MMMP_MAX_OBSTACLES];
+    double obs[MMMP_MAX_OBSTACLES][4];
+    double joint_link_radius;
+};
+
+enum { MMMP_WORLD_SPATIAL = 1, MMMP_WORLD_PLANAR = 2 };
+
+struct mmmp_world {
+    int kind;
+    int device;
+    WorldDev* spatial_d;   // device copy
+    WorldDev* spatial_h;   // host mirror (pinned not required)
+    PlanarDev* planar_d;
+    PlanarDev* planar_h;
+};
+
+#define MMMP_PLANAR_MAX_LINKS 32
+
+// ---------------------------------------------------------------- affine helpers
+struct Affine {  // row-major 3x4
+    float m[12];
+};
+
+__device__ __forceinline__ void affine_load(Affine& T, const float* __restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T.m[i] = p[i];
+}
+
+// T <- T * O * Rz(q)   (O a fixed 3x4 transform, then a rotation about the new z)
+__device__ __forceinline__ void affine_step(Affine& T, const float* __restrict__ O, float s, float c) {
+    float r[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = T.m[4 * i + 0], b = T.m[4 * i + 1], d = T.m[4 * i + 2];
+        r[4 * i + 0] = fmaf(a, O[0], fmaf(b, O[4], d * O[8]));
+        r[4 * i + 1] = fmaf(a, O[1], fmaf(b, O[5], d * O[9]));
+        r[4 * i + 2] = fmaf(a, O[2], fmaf(b, O[6], d * O[10]));
+        r[4 * i + 3] = fmaf(a, O[3], fmaf(b, O[7], fmaf(d, O[11], T.m[4 * i + 3])));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float x = r[4 * i + 0], y = r[4 * i + 1];
+        T.m[4 * i + 0] = fmaf(x, c, y * s);
+        T.m[4 * i + 1] = fmaf(y, c, -x * s);
+        T.m[4 * i + 2] = r[4 * i + 2];
+        T.m[4 * i + 3] = r[4 * i + 3];
+    }
+}
+
+// T <- T * O (fixed transform only, used for the tip frame)
+__device__ __forceinline__ void affine_mul(Affine& T, const float* __restrict__ O) {
+    float r[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = T.m[4 * i + 0], b = T.m[4 * i + 1], d = T.m[4 * i + 2];
+        r[4 * i + 0] = fmaf(a, O[0], fmaf(b, O[4], d * O[8]));
+        r[4 * i + 1] = fmaf(a, O[1], fmaf(b, O[5], d * O[9]));
+        r[4 * i + 2] = fmaf(a, O[2], fmaf(b, O[6], d * O[10]));
+        r[4 * i + 3] = fmaf(a, O[3], fmaf(b, O[7], fmaf(d, O[11], T.m[4 * i + 3])));
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T.m[i] = r[i];
+}
+
+__device__ __forceinline__ float3 affine_point(const Affine& T, float x, float y, float z) {
+    float3 o;
+    o.x = fmaf(T.m[0], x, fmaf(T.m[1], y, fmaf(T.m[2], z, T.m[3])));
+    o.y = fmaf(T.m[4], x, fmaf(T.m[5], y, fmaf(T.m[6], z, T.m[7])));
+    o.z = fmaf(T.m[8], x, fmaf(T.m[9], y, fmaf(T.m[10], z, T.m[11])));
+    return o;
+}
+
+static inline int mmmp_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,202 @@
+// Kernel (b): batched forward kinematics, one configuration per thread, chain
+// constants (base pose + per-joint fixed transforms) staged in shared memory.
+//
+// Reference: Panda.modified_homogeneous_transform / forward_kinematics /
+// positions_from_fk robots/panda.py:111-173 (T = T_base * prod_i T_i(a,d,alpha,q_i),
+// row 7 = fixed flange); the generic URDF chain pybullet evaluates behind
+// resetJointState (utils/pb_joint_utils.py:76-88) for the KUKA iiwa.
+#include "common.cuh"
+
+namespace {
+
+struct ChainSmem {
+    int n_joints;
+    float base[12];
+    float origin[MMMP_MAX_JOINTS + 1][12];
+};
+
+__global__ void __launch_bounds__(256)
+fk_chain_kernel(const WorldDev* __restrict__ W, int robot, const float* __restrict__ q, int ld, int64_t N,
+                float* __restrict__ out_pos, float* __restrict__ out_T) {
+    __shared__ ChainSmem C;
+    {
+        const RobotDev& R = W->robots[robot];
+        if (threadIdx.x == 0) C.n_joints = R.n_joints;
+        for (int i = threadIdx.x; i < 12; i += blockDim.x) C.base[i] = R.base[i];
+        for (int i = threadIdx.x; i < 12 * (MMMP_MAX_JOINTS + 1); i += blockDim.x)
+            (&C.origin[0][0])[i] = (&R.origin[0][0])[i];
+    }
+    __syncthreads();
+    const int n = C.n_joints;
+    const int L = n + 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        Affine T;
+        affine_load(T, C.base);
+        const float* qi = q + i * ld;
+        for (int j = 0; j < n; ++j) {
+            float s, c;
+            sincosf(qi[j], &s, &c);
+            affine_step(T, C.origin[j], s, c);
+            float* p = out_pos + (i * L + j) * 3;
+            p[0] = T.m[3];
+            p[1] = T.m[7];
+            p[2] = T.m[11];
+            if (out_T) {
+                float* t = out_T + (i * L + j) * 12;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) t[k] = T.m[k];
+            }
+        }
+        affine_mul(T, C.origin[n]);
+        float* p = out_pos + (i * L + n) * 3;
+        p[0] = T.m[3];
+        p[1] = T.m[7];
+        p[2] = T.m[11];
+        if (out_T) {
+            float* t = out_T + (i * L + n) * 12;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) t[k] = T.m[k];
+        }
+    }
+}
+
+struct FrameSel {
+    int n;
+    int frame[MMMP_MAX_GROUPS];  // 1-based frame numbers (tip = n_joints + 1)
+};
+
+// FK-metric feature rows: xyz of the selected frames, zero padded to ldf
+__global__ void __launch_bounds__(256)
+fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __restrict__ q, int ld, int64_t N,
+                   FrameSel sel, float* __restrict__ out, int ldf) {
+    __shared__ ChainSmem C;
+    {
+        const RobotDev& R = W->robots[robot];
+        if (threadIdx.x == 0) C.n_joints = R.n_joints;
+        for (int i = threadIdx.x; i < 12; i += blockDim.x) C.base[i] = R.base[i];
+        for (int i = threadIdx.x; i < 12 * (MMMP_MAX_JOINTS + 1); i += blockDim.x)
+            (&C.origin[0][0])[i] = (&R.origin[0][0])[i];
+    }
+    __syncthreads();
+    const int n = C.n_joints;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        Affine T;
+        affine_load(T, C.base);
+        const float* qi = q + i * ld;
+        float* o = out + i * ldf;
+        for (int j = 0; j <= n; ++j) {
+            if (j < n) {
+                float s, c;
+                sincosf(qi[j], &s, &c);
+                affine_step(T, C.origin[j], s, c);
+            } else {
+                affine_mul(T, C.origin[n]);
+            }
+            for (int g = 0; g < sel.n; ++g)
+                if (sel.frame[g] == j + 1) {
+                    o[3 * g + 0] = T.m[3];
+                    o[3 * g + 1] = T.m[7];
+                    o[3 * g + 2] = T.m[11];
+                }
+        }
+        for (int c = 3 * sel.n; c < ldf; ++c) o[c] = 0.f;
+    }
+}
+
+// fp64 twin, non-fused arithmetic in the reference's matmul order
+// (np.matmul(T, T_i) row by column, k ascending): used for the fp64 re-rank of
+// neighbour candidates, where the metric must follow robots/panda.py:248-254.
+__global__ void __launch_bounds__(128)
+fk_chain_f64_kernel(const WorldDev* __restrict__ W, int robot, const double* __restrict__ q, int ld, int64_t N,
+                    double* __restrict__ out_pos) {
+    __shared__ RobotDev64 C;
+    for (int i = threadIdx.x; i < (int)(sizeof(RobotDev64) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(&C)[i] = reinterpret_cast<const int*>(&W->robots64[robot])[i];
+    __syncthreads();
+    const int n = C.n_joints;
+    const int L = n + 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        double T[12];
+        for (int k = 0; k < 12; ++k) T[k] = C.base[k];
+        const double* qi = q + i * ld;
+        for (int j = 0; j <= n; ++j) {
+            // M = O * Rz(q): the reference builds T_i in one go (panda.py:111-122);
+            // its entries are products of two factors, so O*Rz with exact 0/1
+            // entries of Rz reproduces them up to the rounding of ct*ca etc.
+            const double* O = C.origin[j];
+            double s = 0.0, c = 1.0;
+            if (j < n) sincos(qi[j], &s, &c);
+            double M[12];
+            for (int r = 0; r < 3; ++r) {
+                M[4 * r + 0] = __dadd_rn(__dmul_rn(O[4 * r + 0], c), __dmul_rn(O[4 * r + 1], s));
+                M[4 * r + 1] = __dsub_rn(__dmul_rn(O[4 * r + 1], c), __dmul_rn(O[4 * r + 0], s));
+                M[4 * r + 2] = O[4 * r + 2];
+                M[4 * r + 3] = O[4 * r + 3];
+            }
+            double Rr[12];
+            for (int r = 0; r < 3; ++r) {
+                for (int cc = 0; cc < 4; ++cc) {
+                    double acc = __dmul_rn(T[4 * r + 0], M[cc]);
+                    acc = __dadd_rn(acc, __dmul_rn(T[4 * r + 1], M[4 + cc]));
+                    acc = __dadd_rn(acc, __dmul_rn(T[4 * r + 2], M[8 + cc]));
+                    if (cc == 3) acc = __dadd_rn(acc, T[4 * r + 3]);
+                    Rr[4 * r + cc] = acc;
+                }
+            }
+            for (int k = 0; k < 12; ++k) T[k] = Rr[k];
+            double* p = out_pos + (i * L + j) * 3;
+            p[0] = T[3];
+            p[1] = T[7];
+            p[2] = T[11];
+        }
+    }
+}
+
+int fk_grid(int64_t N, int block) {
+    int64_t g = (N + block - 1) / block;
+    const int64_t cap = 148 * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int mmmp_fk_chain(const mmmp_world* w, int robot, const float* q, int ld, int64_t N, float* out_pos,
+                             float* out_T, void* stream) {
+    if (!w || !q || !out_pos || N < 0) return MMMP_ERR_ARG;
+    if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
+    if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
+    if (N == 0) return MMMP_OK;
+    MMMP_LAUNCH(fk_chain_kernel, fk_grid(N, 256), 256, 0, stream, w->spatial_d, robot, q, ld, N, out_pos, out_T);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_fk_chain_f64(const mmmp_world* w, int robot, const double* q, int ld, int64_t N,
+                                 double* out_pos, void* stream) {
+    if (!w || !q || !out_pos || N < 0) return MMMP_ERR_ARG;
+    if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
+    if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
+    if (N == 0) return MMMP_OK;
+    MMMP_LAUNCH(fk_chain_f64_kernel, fk_grid(N, 128), 128, 0, stream, w->spatial_d, robot, q, ld, N, out_pos);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_fk_features(const mmmp_world* w, int robot, const float* q, int ld, int64_t N,
+                                const int32_t* frames, int n_frames, float* out, int ldf, void* stream) {
+    if (!w || !q || !out || !frames || N < 0) return MMMP_ERR_ARG;
+    if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
+    if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
+    if (n_frames < 1 || n_frames > MMMP_MAX_GROUPS || ldf < 3 * n_frames) return MMMP_ERR_ARG;
+    FrameSel sel;
+    sel.n = n_frames;
+    for (int g = 0; g < MMMP_MAX_GROUPS; ++g) sel.frame[g] = -1;
+    for (int g = 0; g < n_frames; ++g) {
+        if (frames[g] < 1 || frames[g] > w->spatial_h->robots[robot].n_joints + 1) return MMMP_ERR_ARG;
+        sel.frame[g] = frames[g];
+    }
+    if (N == 0) return MMMP_OK;
+    MMMP_LAUNCH(fk_features_kernel, fk_grid(N, 256), 256, 0, stream, w->spatial_d, robot, q, ld, N, sel, out, ldf);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}

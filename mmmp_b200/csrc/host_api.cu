@@ -1,0 +1,244 @@
+// Host-buffer entry points: the call a reference-side planner makes with numpy
+// arrays (host memory in, host memory out), and the native host replay of the
+// order-dependent greedy accept pass.
+//
+// Reference: DecoupledPRM.generate_roadmap decoupled_prm.py:231-260,
+// sample_valid_in_joint_space_random :310-321, connect_nearest_neighbors_degree
+// :480-504, is_collision_free_sample / _edge :840-863.
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+
+namespace {
+
+// edges[e] = (e / k, nbr[e]) for the flat [n, k] neighbour table
+__global__ void __launch_bounds__(256)
+edges_from_knn_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int32_t* __restrict__ edges) {
+    const int64_t total = n * k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        edges[2 * e] = (int32_t)(e / k);
+        edges[2 * e + 1] = nbr[e];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+invert_flags_kernel(uint8_t* f, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        f[i] = f[i] ? 0 : 1;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    template <class T>
+    T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+extern "C" int mmmp_edges_from_knn(const int32_t* nbr_d, int64_t n, int k, int32_t* edges_d, void* stream) {
+    if (!nbr_d || !edges_d || n < 0 || k < 1) return MMMP_ERR_ARG;
+    if (n == 0) return MMMP_OK;
+    int g = mmmp_div_up(n * k, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    MMMP_LAUNCH(edges_from_knn_kernel, g, 256, 0, stream, nbr_d, n, k, edges_d);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}
+
+
+// Frames whose origin depends on q, with coincident consecutive frames merged
+// (multiplicity = group weight).  Frame f (1-based, tip = n_joints+1) sits at
+// p_f = p_{f-1} + R_{f-1} t_{f-1}; it is q-independent while t_1..t_{f-1} are all
+// zero and coincides with frame f-1 when t_{f-1} is zero.  Panda (robots/panda.py:31-40):
+// frames 3,4,6(x2),7,8 -> weights 1,1,2,1,1.
+extern "C" int mmmp_fk_metric_groups(const mmmp_world* w, int robot, int32_t* frames, float* weights, int* n_groups) {
+    if (!w || !frames || !weights || !n_groups) return MMMP_ERR_ARG;
+    if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
+    if (robot < 0 || robot >= w->spatial_h->n_robots) return MMMP_ERR_ARG;
+    const RobotDev64& C = w->spatial_h->robots64[robot];
+    const int L = C.n_joints + 1;
+    auto zero_t = [&](int j) { return C.origin[j][3] == 0.0 && C.origin[j][7] == 0.0 && C.origin[j][11] == 0.0; };
+    int ng = 0;
+    for (int f = 1; f <= L; ++f) {
+        bool moves = false;
+        for (int g = 1; g < f; ++g)
+            if (!zero_t(g)) moves = true;
+        if (!moves) continue;
+        if (zero_t(f - 1) && ng > 0 && frames[ng - 1] == f - 1) {
+            frames[ng - 1] = f;
+            weights[ng - 1] += 1.f;
+            continue;
+        }
+        if (ng == MMMP_MAX_GROUPS) return MMMP_ERR_LIMIT;
+        frames[ng] = f;
+        weights[ng] = 1.f;
+        ++ng;
+    }
+    if (ng == 0) return MMMP_ERR_ARG;
+    *n_groups = ng;
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D,
+                                            int metric_kind, int k, int n_steps, double step, uint32_t flags,
+                                            int64_t* n_nodes_h, int32_t* node_src_h, int32_t* nbr_idx_h,
+                                            double* nbr_dist_h, uint8_t* edge_free_h, float* timings_ms_h) {
+    if (!w || !q64_h || !n_nodes_h || !node_src_h || !nbr_idx_h || !edge_free_h) return MMMP_ERR_ARG;
+    if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
+    if (N < 1 || D < 1 || k < 1 || k > MMMP_MAX_K) return MMMP_ERR_ARG;
+    if (robot < 0 || robot >= w->spatial_h->n_robots) return MMMP_ERR_ARG;
+    const int nj = w->spatial_h->robots[robot].n_joints;
+    if (D != nj) return MMMP_ERR_ARG;
+    if (metric_kind != MMMP_METRIC_L2 && metric_kind != MMMP_METRIC_GROUP_L2_SUM) return MMMP_ERR_KIND;
+    const int ld32 = (D + 3) & ~3;
+    int kc = k + 6;
+    if (kc > MMMP_MAX_K) kc = MMMP_MAX_K;
+
+    cudaStream_t s;
+    MMMP_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaEvent_t ev[9];
+    for (auto& e : ev) cudaEventCreate(&e);
+    int rc = MMMP_OK;
+    int64_t n_nodes = 0;
+    {
+        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, pos64, cidx, cdist, ridx, rdist, edges, ecoll;
+        const int L = nj + 1;
+        auto T = [&](cudaError_t e) {
+            if (e != cudaSuccess && rc == MMMP_OK) rc = MMMP_ERR_CUDA_BASE + (int)e;
+        };
+        auto R = [&](int r) {
+            if (r != MMMP_OK && rc == MMMP_OK) rc = r;
+        };
+        T(q64.alloc(sizeof(double) * N * D));
+        T(q32.alloc(sizeof(float) * N * ld32));
+        T(coll.alloc(N));
+        T(idx.alloc(sizeof(int32_t) * N));
+        T(cnt.alloc(sizeof(int32_t)));
+        if (rc == MMMP_OK) {
+            cudaEventRecord(ev[0], s);
+            T(cudaMemcpyAsync(q64.p, q64_h, sizeof(double) * N * D, cudaMemcpyHostToDevice, s));
+            cudaEventRecord(ev[1], s);
+            R(mmmp_pack_f32(q64.as<double>(), D, D, N, q32.as<float>(), ld32, s));
+            R(mmmp_collide_configs(w, robot, q32.p, ld32, N, flags, coll.as<uint8_t>(), s));
+            R(mmmp_compact_free(coll.as<uint8_t>(), N, idx.as<int32_t>(), cnt.as<int32_t>(), s));
+            int32_t c = 0;
+            T(cudaMemcpyAsync(&c, cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            T(cudaStreamSynchronize(s));
+            n_nodes = c;
+        }
+        if (rc == MMMP_OK && n_nodes > 0) {
+            const int64_t n = n_nodes;
+            T(nq64.alloc(sizeof(double) * n * D));
+            T(nq32.alloc(sizeof(float) * n * ld32));
+            T(cidx.alloc(sizeof(int32_t) * n * kc));
+            T(cdist.alloc(sizeof(float) * n * kc));
+            T(ridx.alloc(sizeof(int32_t) * n * k));
+            T(rdist.alloc(sizeof(double) * n * k));
+            T(edges.alloc(sizeof(int32_t) * n * k * 2));
+            T(ecoll.alloc(n * k));
+            mmmp_metric m32, m64;
+            memset(&m32, 0, sizeof(m32));
+            memset(&m64, 0, sizeof(m64));
+            const float* feat_ptr = nullptr;
+            const double* ref64_ptr = nullptr;
+            int ldf = ld32, ld64 = D;
+            if (rc == MMMP_OK) {
+                R(mmmp_gather_rows(q64.p, (int)(sizeof(double) * D), idx.as<int32_t>(), n, nq64.p, s));
+                R(mmmp_gather_rows(q32.p, (int)(sizeof(float) * ld32), idx.as<int32_t>(), n, nq32.p, s));
+                cudaEventRecord(ev[2], s);
+                if (metric_kind == MMMP_METRIC_L2) {
+                    m32.kind = m64.kind = MMMP_METRIC_L2;
+                    m32.dim = m64.dim = D;
+                    feat_ptr = nq32.as<float>();
+                    ref64_ptr = nq64.as<double>();
+                } else {
+                    int frames[MMMP_MAX_GROUPS];
+                    float wts[MMMP_MAX_GROUPS];
+                    int ng = 0;
+                    R(mmmp_fk_metric_groups(w, robot, frames, wts, &ng));
+                    if (rc == MMMP_OK && ng == 0) rc = MMMP_ERR_ARG;
+                    ldf = (3 * ng + 3) & ~3;
+                    m32.kind = MMMP_METRIC_GROUP_L2_SUM;
+                    m32.dim = 3 * ng;
+                    m32.n_groups = ng;
+                    for (int g = 0; g < ng; ++g) m32.weight[g] = wts[g];
+                    m64.kind = MMMP_METRIC_GROUP_L2_SUM;
+                    m64.dim = 3 * L;
+                    m64.n_groups = L;
+                    ld64 = 3 * L;
+                    T(feat.alloc(sizeof(float) * n * ldf));
+                    T(pos64.alloc(sizeof(double) * n * 3 * L));
+                    if (rc == MMMP_OK) {
+                        R(mmmp_fk_features(w, robot, nq32.as<float>(), ld32, n, frames, ng, feat.as<float>(), ldf, s));
+                        R(mmmp_fk_chain_f64(w, robot, nq64.as<double>(), D, n, pos64.as<double>(), s));
+                    }
+                    feat_ptr = feat.as<float>();
+                    ref64_ptr = pos64.as<double>();
+                }
+                cudaEventRecord(ev[3], s);
+            }
+            if (rc == MMMP_OK) {
+                R(mmmp_knn(feat_ptr, n, feat_ptr, n, ldf, &m32, kc, 1, 0, 0, cidx.as<int32_t>(), cdist.as<float>(), s));
+                cudaEventRecord(ev[4], s);
+                R(mmmp_knn_refine(ref64_ptr, ref64_ptr, ld64, &m64, cidx.as<int32_t>(), cdist.as<float>(), n, kc, k,
+                                  1e-6, ridx.as<int32_t>(), rdist.as<double>(), nullptr, s));
+                cudaEventRecord(ev[5], s);
+                R(mmmp_edges_from_knn(ridx.as<int32_t>(), n, k, edges.as<int32_t>(), s));
+                R(mmmp_collide_edges(w, robot, nq32.p, ld32, edges.as<int32_t>(), n * k, n_steps, step, flags,
+                                     ecoll.as<uint8_t>(), s));
+                int g = mmmp_div_up(n * k, 256);
+                if (g > 148 * 16) g = 148 * 16;
+                MMMP_LAUNCH(invert_flags_kernel, g, 256, 0, s, ecoll.as<uint8_t>(), n * k);
+                cudaEventRecord(ev[6], s);
+                T(cudaMemcpyAsync(node_src_h, idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+                T(cudaMemcpyAsync(nbr_idx_h, ridx.p, sizeof(int32_t) * n * k, cudaMemcpyDeviceToHost, s));
+                if (nbr_dist_h) T(cudaMemcpyAsync(nbr_dist_h, rdist.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, s));
+                T(cudaMemcpyAsync(edge_free_h, ecoll.p, (size_t)n * k, cudaMemcpyDeviceToHost, s));
+                cudaEventRecord(ev[7], s);
+                T(cudaStreamSynchronize(s));
+                if (rc == MMMP_OK && timings_ms_h) {
+                    for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&timings_ms_h[i], ev[i], ev[i + 1]);
+                    cudaEventElapsedTime(&timings_ms_h[7], ev[0], ev[7]);
+                }
+            }
+        }
+    }
+    *n_nodes_h = n_nodes;
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+// Greedy accept pass, reference decoupled_prm.py:480-504: nodes in id order,
+// candidates ascending (dist,id); stop when deg[node]==k2; accept iff the edge
+// is free, not already present, and (cap_other_end) deg[neighbour] != k2.
+extern "C" int mmmp_greedy_degree_connect(const int32_t* nbr_idx, const uint8_t* edge_free, int64_t N, int k1,
+                                          int k2, int cap, int32_t* adj, int32_t* deg) {
+    if (!nbr_idx || !edge_free || !adj || !deg || N < 0 || k1 < 1 || k2 < 1 || cap < k2) return MMMP_ERR_ARG;
+    for (int64_t i = 0; i < N; ++i) deg[i] = 0;
+    for (int64_t i = 0; i < N * (int64_t)cap; ++i) adj[i] = -1;
+    for (int64_t i = 0; i < N; ++i) {
+        for (int c = 0; c < k1; ++c) {
+            if (deg[i] == k2) break;
+            const int32_t j = nbr_idx[i * k1 + c];
+            if (j < 0 || j >= N) continue;
+            if (!edge_free[i * k1 + c]) continue;
+            bool present = false;
+            for (int t = 0; t < deg[i]; ++t)
+                if (adj[i * cap + t] == j) {
+                    present = true;
+                    break;
+                }
+            if (present) continue;
+            if (deg[j] == k2) continue;
+            if (deg[i] >= cap || deg[j] >= cap) return MMMP_ERR_LIMIT;
+            adj[i * cap + deg[i]++] = j;
+            adj[(int64_t)j * cap + deg[j]++] = (int32_t)i;
+        }
+    }
+    return MMMP_OK;
+}

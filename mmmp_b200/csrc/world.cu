@@ -1,0 +1,333 @@
+// World (scene) tables: host descriptors -> device-resident constant tables.
+// Replaces the state pybullet keeps behind loadURDF / the planar Environment
+// object (reference: robots/robot.py:19-28, planners/prm/pybullet/env.py:15-29,
+// planners/prm/planar/env.py:21-47).
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include "common.cuh"
+#include "obstacle.cuh"
+
+std::atomic<int64_t> g_mmmp_launches{0};
+
+// q-independent part: spheres of frame-0 links (already in world coordinates)
+// against every obstacle primitive.  One thread per robot.
+__global__ void world_static_kernel(WorldDev* W) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= W->n_robots) return;
+    RobotDev& R = W->robots[r];
+    int hit = 0;
+    for (int l = 0; l < R.n_links; ++l) {
+        if (R.link_frame[l] != 0) continue;
+        for (int s = R.link_sphere_begin[l]; s < R.link_sphere_begin[l + 1]; ++s) {
+            const float4 sp = R.sphere[s];
+            for (int o = 0; o < W->n_obstacles; ++o)
+                hit |= sphere_hits_obstacle(sp.x, sp.y, sp.z, sp.w, W->obstacles[o]) ? 1 : 0;
+        }
+    }
+    R.base_hits_obstacles = hit;
+}
+
+static void affine_point_d(const double* T, const double* p, double* o) {
+    for (int i = 0; i < 3; ++i) o[i] = T[4 * i] * p[0] + T[4 * i + 1] * p[1] + T[4 * i + 2] * p[2] + T[4 * i + 3];
+}
+
+// bounding sphere of a set of spheres (Ritter pass over centres, then inflate)
+static void bounding_sphere(const float4* sp, int n, float4* out) {
+    if (n <= 0) {
+        *out = make_float4(0.f, 0.f, 0.f, -1.f);
+        return;
+    }
+    double c[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        c[0] += sp[i].x;
+        c[1] += sp[i].y;
+        c[2] += sp[i].z;
+    }
+    for (int k = 0; k < 3; ++k) c[k] /= n;
+    // a few Badoiu-Clarkson steps on the inflated extent
+    for (int it = 0; it < 64; ++it) {
+        int far = 0;
+        double fd = -1;
+        for (int i = 0; i < n; ++i) {
+            const double d = std::sqrt((sp[i].x - c[0]) * (sp[i].x - c[0]) + (sp[i].y - c[1]) * (sp[i].y - c[1]) +
+                                       (sp[i].z - c[2]) * (sp[i].z - c[2])) + sp[i].w;
+            if (d > fd) {
+                fd = d;
+                far = i;
+            }
+        }
+        const double t = 1.0 / (it + 2);
+        c[0] += (sp[far].x - c[0]) * t;
+        c[1] += (sp[far].y - c[1]) * t;
+        c[2] += (sp[far].z - c[2]) * t;
+    }
+    double r = 0;
+    for (int i = 0; i < n; ++i) {
+        const double d = std::sqrt((sp[i].x - c[0]) * (sp[i].x - c[0]) + (sp[i].y - c[1]) * (sp[i].y - c[1]) +
+                                   (sp[i].z - c[2]) * (sp[i].z - c[2])) + sp[i].w;
+        if (d > r) r = d;
+    }
+    *out = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(r * (1.0 + 1e-6) + 1e-7));
+}
+
+extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
+                                 const mmmp_obstacle_desc* obstacles, int n_obstacles,
+                                 mmmp_world** out) {
+    if (!out || !robots || n_robots < 1 || (n_obstacles > 0 && !obstacles)) return MMMP_ERR_ARG;
+    if (n_robots > MMMP_MAX_ROBOTS || n_obstacles > MMMP_MAX_OBSTACLES || n_obstacles < 0) return MMMP_ERR_LIMIT;
+    WorldDev* H = (WorldDev*)calloc(1, sizeof(WorldDev));
+    if (!H) return MMMP_ERR_ARG;
+    H->n_robots = n_robots;
+    H->n_obstacles = n_obstacles;
+    int dof = 0;
+    int table_words = 0;
+    const int pool_words = (int)(sizeof(H->table_bits) / sizeof(unsigned int));
+    for (int r = 0; r < n_robots; ++r) {
+        const mmmp_robot_desc& d = robots[r];
+        RobotDev& R = H->robots[r];
+        RobotDev64& R64 = H->robots64[r];
+        if (d.n_joints < 1 || d.n_joints > MMMP_MAX_JOINTS || d.n_spheres < 0 ||
+            d.n_spheres > MMMP_MAX_SPHERES || d.n_links < 0 || d.n_links > MMMP_MAX_LINKS ||
+            d.n_pair_tables < 0 || d.n_pair_tables > MMMP_MAX_PAIR_TABLES) {
+            free(H);
+            return MMMP_ERR_LIMIT;
+        }
+        R.n_joints = d.n_joints;
+        R.n_spheres = d.n_spheres;
+        R.n_links = d.n_links;
+        R.dof_offset = d.dof_offset;
+        R64.n_joints = d.n_joints;
+        for (int i = 0; i < 12; ++i) {
+            R.base[i] = (float)d.base[i];
+            R64.base[i] = d.base[i];
+        }
+        for (int j = 0; j <= d.n_joints; ++j)
+            for (int i = 0; i < 12; ++i) {
+                R.origin[j][i] = (float)d.origin[j][i];
+                R64.origin[j][i] = d.origin[j][i];
+            }
+        // spheres sorted by link; link_sphere_begin[l] = #spheres with link < l
+        for (int l = 0; l <= MMMP_MAX_LINKS; ++l) R.link_sphere_begin[l] = 0;
+        int prev = 0;
+        for (int l = 0; l < d.n_links; ++l) {
+            if (d.link_frame[l] < 0 || d.link_frame[l] > d.n_joints) {
+                free(H);
+                return MMMP_ERR_ARG;
+            }
+            R.link_frame[l] = d.link_frame[l];
+        }
+        for (int s = 0; s < d.n_spheres; ++s) {
+            const int l = d.sphere_link[s];
+            if (l < prev || l >= d.n_links) {
+                free(H);
+                return MMMP_ERR_ARG;
+            }
+            prev = l;
+            for (int g = l + 1; g <= MMMP_MAX_LINKS; ++g) R.link_sphere_begin[g]++;
+            if (d.link_frame[l] == 0) {  // base link: store world coordinates
+                double o[3];
+                affine_point_d(d.base, d.sphere[s], o);
+                R.sphere[s] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)d.sphere[s][3]);
+            } else {
+                R.sphere[s] = make_float4((float)d.sphere[s][0], (float)d.sphere[s][1],
+                                          (float)d.sphere[s][2], (float)d.sphere[s][3]);
+            }
+        }
+        R.n_moving_links = 0;
+        for (int l = 0; l < d.n_links; ++l) {
+            bounding_sphere(R.sphere + R.link_sphere_begin[l], R.link_sphere_begin[l + 1] - R.link_sphere_begin[l],
+                            &R.link_bound[l]);
+            if (R.link_frame[l] != 0) R.n_moving_links++;
+        }
+        // exact pair tables (deduplicated across robots by content)
+        unsigned int table_mask[MMMP_MAX_LINKS];
+        for (int l = 0; l < MMMP_MAX_LINKS; ++l) table_mask[l] = 0;
+        R.n_tables = d.n_pair_tables;
+        for (int t = 0; t < d.n_pair_tables; ++t) {
+            const mmmp_pair_table& pt = d.pair_table[t];
+            const int64_t cells = (int64_t)pt.n_u * pt.n_v;
+            if (pt.n_u < 1 || pt.n_v < 1 || cells > (int64_t)MMMP_PAIR_TABLE_WORDS * 32 || pt.joint_u < 0 ||
+                pt.joint_v < 0 || pt.joint_u >= d.n_joints || pt.joint_v >= d.n_joints || pt.link_a < 0 ||
+                pt.link_b < 0 || pt.link_a >= d.n_links || pt.link_b >= d.n_links || !(pt.hi_u > pt.lo_u) ||
+                !(pt.hi_v > pt.lo_v)) {
+                free(H);
+                return MMMP_ERR_ARG;
+            }
+            const int words = (int)((cells + 31) / 32);
+            int off = -1;
+            for (int o = 0; o + words <= table_words && off < 0; ++o)
+                if (memcmp(H->table_bits + o, pt.bits, sizeof(unsigned int) * words) == 0) off = o;
+            if (off < 0) {
+                if (table_words + words > pool_words) {
+                    free(H);
+                    return MMMP_ERR_LIMIT;
+                }
+                off = table_words;
+                memcpy(H->table_bits + off, pt.bits, sizeof(unsigned int) * words);
+                table_words += words;
+            }
+            PairTableDev& T = R.table[t];
+            T.joint_u = pt.joint_u;
+            T.joint_v = pt.joint_v;
+            T.n_u = pt.n_u;
+            T.n_v = pt.n_v;
+            T.lo_u = (float)pt.lo_u;
+            T.lo_v = (float)pt.lo_v;
+            T.inv_du = (float)(pt.n_u / (pt.hi_u - pt.lo_u));
+            T.inv_dv = (float)(pt.n_v / (pt.hi_v - pt.lo_v));
+            T.word_offset = off;
+            table_mask[pt.link_a] |= 1u << pt.link_b;
+            table_mask[pt.link_b] |= 1u << pt.link_a;
+        }
+        // self-collision link pairs from the mask, minus the pairs a table decides
+        R.n_self_pairs = 0;
+        for (int a = 0; a < d.n_links; ++a)
+            for (int b = a + 1; b < d.n_links; ++b) {
+                const bool on = ((d.self_mask[a] >> b) & 1u) || ((d.self_mask[b] >> a) & 1u);
+                if (!on || ((table_mask[a] >> b) & 1u)) continue;
+                if (R.link_frame[a] == 0 && R.link_frame[b] == 0) continue;  // static pair
+                if (R.link_sphere_begin[a + 1] == R.link_sphere_begin[a] ||
+                    R.link_sphere_begin[b + 1] == R.link_sphere_begin[b])
+                    continue;
+                R.self_pair[R.n_self_pairs++] = make_uchar2((unsigned char)a, (unsigned char)b);
+            }
+        if (d.dof_offset + d.n_joints > dof) dof = d.dof_offset + d.n_joints;
+    }
+    H->dof = dof;
+    H->n_table_words = table_words;
+    for (int o = 0; o < n_obstacles; ++o) {
+        ObstacleDev& O = H->obstacles[o];
+        O.type = obstacles[o].type;
+        O.body = obstacles[o].body;
+        if (O.type < MMMP_OBS_PLANE || O.type > MMMP_OBS_CYLINDER) {
+            free(H);
+            return MMMP_ERR_KIND;
+        }
+        for (int i = 0; i < 16; ++i) O.p[i] = (float)obstacles[o].p[i];
+    }
+    mmmp_world* w = new (std::nothrow) mmmp_world();
+    if (!w) {
+        free(H);
+        return MMMP_ERR_ARG;
+    }
+    w->kind = MMMP_WORLD_SPATIAL;
+    w->spatial_h = H;
+    w->spatial_d = nullptr;
+    w->planar_d = nullptr;
+    w->planar_h = nullptr;
+    cudaError_t e = cudaGetDevice(&w->device);
+    if (e == cudaSuccess) e = cudaMalloc(&w->spatial_d, sizeof(WorldDev));
+    if (e == cudaSuccess) e = cudaMemcpy(w->spatial_d, H, sizeof(WorldDev), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        MMMP_LAUNCH(world_static_kernel, 1, 32, 0, 0, w->spatial_d);
+        e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpy(H, w->spatial_d, sizeof(WorldDev), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        if (w->spatial_d) cudaFree(w->spatial_d);
+        free(H);
+        delete w;
+        return MMMP_ERR_CUDA_BASE + (int)e;
+    }
+    *out = w;
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_planar_world_create(const mmmp_planar_desc* d, mmmp_world** out) {
+    if (!out || !d) return MMMP_ERR_ARG;
+    if (d->n_arms < 1 || d->n_arms > MMMP_MAX_ROBOTS || d->n_obstacles < 0 ||
+        d->n_obstacles > MMMP_MAX_OBSTACLES)
+        return MMMP_ERR_LIMIT;
+    PlanarDev* H = (PlanarDev*)calloc(1, sizeof(PlanarDev));
+    if (!H) return MMMP_ERR_ARG;
+    H->n_arms = d->n_arms;
+    H->n_obstacles = d->n_obstacles;
+    int dof = 0, links = 0;
+    for (int a = 0; a < d->n_arms; ++a) {
+        if (d->n_links[a] < 1 || d->n_links[a] > MMMP_MAX_JOINTS) {
+            free(H);
+            return MMMP_ERR_LIMIT;
+        }
+        H->n_links[a] = d->n_links[a];
+        H->dof_offset[a] = d->dof_offset[a];
+        H->link_begin[a] = links;
+        links += d->n_links[a];
+        if (d->dof_offset[a] + d->n_links[a] > dof) dof = d->dof_offset[a] + d->n_links[a];
+        for (int l = 0; l < d->n_links[a]; ++l) H->link_len[a][l] = d->link_len[a][l];
+        H->base[a][0] = d->base[a][0];
+        H->base[a][1] = d->base[a][1];
+    }
+    if (links > MMMP_PLANAR_MAX_LINKS) {
+        free(H);
+        return MMMP_ERR_LIMIT;
+    }
+    H->link_begin[d->n_arms] = links;
+    H->total_links = links;
+    H->dof = dof;
+    for (int i = 0; i < 4; ++i) H->bounds[i] = d->bounds[i];
+    for (int o = 0; o < d->n_obstacles; ++o) {
+        if (d->obs_type[o] != MMMP_POBS_RECT && d->obs_type[o] != MMMP_POBS_CIRCLE) {
+            free(H);
+            return MMMP_ERR_KIND;
+        }
+        H->obs_type[o] = d->obs_type[o];
+        for (int i = 0; i < 4; ++i) H->obs[o][i] = d->obs[o][i];
+    }
+    H->joint_link_radius = d->joint_link_radius;
+    mmmp_world* w = new (std::nothrow) mmmp_world();
+    if (!w) {
+        free(H);
+        return MMMP_ERR_ARG;
+    }
+    w->kind = MMMP_WORLD_PLANAR;
+    w->planar_h = H;
+    w->spatial_d = nullptr;
+    w->spatial_h = nullptr;
+    cudaError_t e = cudaGetDevice(&w->device);
+    if (e == cudaSuccess) e = cudaMalloc(&w->planar_d, sizeof(PlanarDev));
+    if (e == cudaSuccess) e = cudaMemcpy(w->planar_d, H, sizeof(PlanarDev), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (w->planar_d) cudaFree(w->planar_d);
+        free(H);
+        delete w;
+        return MMMP_ERR_CUDA_BASE + (int)e;
+    }
+    *out = w;
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_world_destroy(mmmp_world* w) {
+    if (!w) return MMMP_OK;
+    if (w->spatial_d) cudaFree(w->spatial_d);
+    if (w->planar_d) cudaFree(w->planar_d);
+    free(w->spatial_h);
+    free(w->planar_h);
+    delete w;
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_world_dof(const mmmp_world* w) {
+    if (!w) return -1;
+    return w->kind == MMMP_WORLD_SPATIAL ? w->spatial_h->dof : w->planar_h->dof;
+}
+
+extern "C" int mmmp_version(void) { return 100; }
+
+extern "C" int mmmp_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+    int dev = 0;
+    MMMP_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    MMMP_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    if (clock_khz) *clock_khz = khz;
+    return MMMP_OK;
+}
+
+extern "C" int64_t mmmp_launch_count(void) { return g_mmmp_launches.load(); }

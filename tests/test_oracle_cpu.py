@@ -1,0 +1,141 @@
+"""CPU suite: the oracle restatements against the reference's own outputs
+(tests/golden/*.npz, written by tools/gen_golden.py from the reference itself) and
+against the reference's fixtures / known answers."""
+import numpy as np
+import pytest
+
+from oracle import chain, knn as oknn, planar, sampling
+
+
+def _planar_world(g, n_arms=2):
+    rects = [{"type": "rect", "x0": r[0], "y0": r[1], "x1": r[2], "y1": r[3]} for r in g["w2_rects"]]
+    circ = [{"type": "circle", "cx": c[0], "cy": c[1], "r": c[2]} for c in g["w2_circles"]]
+    arms = [{"links": list(g["w2_links"][i]), "base": tuple(g["w2_bases"][i])} for i in range(n_arms)]
+    return {"arms": arms, "bounds": (-10.0, 10.0, -10.0, 10.0), "obstacles": rects + circ, "joint_link_radius": 0.5}
+
+
+def test_planar_fk_known_answer():
+    # reference tests/robots/test_planar_arm.py:19-26
+    pos = planar.fk([1.0, 1.0], (0.0, 0.0), [np.pi / 2, np.pi / 2])
+    np.testing.assert_almost_equal(np.array(pos), np.array([[0, 1], [-1, 1]]), decimal=5)
+
+
+def test_planar_predicates_match_reference(golden):
+    g = golden("planar_predicates")
+    w = _planar_world(g)
+    q = g["coupled_q"]
+    got = np.array([not planar.config_in_collision(w, s) for s in q[:1500]])
+    assert (got == g["coupled_free"][:1500]).all()
+    rr = np.array([planar.config_in_collision(w, s, bounds=False, self_=False, obstacles=False) for s in q[:1500]])
+    assert (rr == g["rr_hit"]).all()
+    q2 = g["dec_q"]
+    for arm, key in ((0, "dec_free_r0"), (1, "dec_free_r1")):
+        got = np.array([not planar.config_in_collision(w, s, arm=arm, self_=False, robots=False) for s in q2[:800]])
+        assert (got == g[key][:800]).all()
+
+
+def test_planar_edges_match_reference(golden):
+    g = golden("planar_predicates")
+    w = _planar_world(g)
+    q = g["coupled_q"]
+    got = np.array([not planar.edge_in_collision(w, a, b, 0.05) for a, b in zip(q[:150], q[400:550])])
+    assert (got == g["coupled_edge_free"][:150]).all()
+    got = np.array([not planar.edge_in_collision(w, a, b, 0.05) for a, b in zip(q[:150], g["coupled_edge2_b"][:150])])
+    assert (got == g["coupled_edge2_free"][:150]).all()
+
+
+def test_panda_fk_matches_reference(golden):
+    g = golden("panda_fk")
+    for tag in ("id", "b1", "b2"):
+        b = g[f"fk_{tag}_base"]
+        base = chain.base_matrix(b[:3], b[3:])
+        pos = chain.panda_positions(g[f"fk_{tag}_q"], base)
+        assert np.abs(pos - g[f"fk_{tag}_pos"]).max() < 1e-12
+        T = chain.panda_frames(g[f"fk_{tag}_q"], base)[:, 7]
+        assert np.abs(T - g[f"fk_{tag}_T"]).max() < 1e-12
+    q = g["fk_id_q"]
+    d = chain.panda_pose_distance(q[:200], q[200:])
+    assert np.abs(d - g["pose_dist"]).max() < 1e-12
+    # SURVEY 8c known answers: flange at q_ref, and the pair distance
+    q_ref = [0, -np.pi / 4, 0, -3 * np.pi / 4, 0, np.pi / 2, np.pi / 4]
+    assert np.allclose(chain.panda_positions([q_ref])[0, 7], [0.306891, 0.0, 0.590282], atol=1e-6)
+    assert abs(chain.panda_pose_distance([q_ref], [[.1, -.5, .2, -2, .3, 1.5, .7]])[0] - g["known_dist"][0]) < 1e-12
+    assert np.allclose(chain.panda_positions([[0] * 7])[0, 7], [0.088, 0, 0.926], atol=1e-12)
+
+
+def test_generic_chain_equals_dh_chain(golden):
+    from oracle.spheres import model_origins
+    import json, os
+    model = json.load(open(os.path.join(os.path.dirname(__file__), "..", "mmmp_b200", "geometry", "panda_spheres.json")))
+    q = golden("panda_fk")["fk_id_q"][:50]
+    fr = chain.chain_frames(model_origins(model), q, np.eye(4))
+    assert np.abs(fr[:, :, :3, 3] - chain.panda_positions(q)).max() < 1e-12
+
+
+def test_heap_knn_and_greedy_match_reference(golden):
+    g = golden("panda_heap_knn")
+    n12 = np.array([[1, 1], [1, 2], [2, 1], [10, 10], [11, 10], [10, 11], [20, 20], [21, 20], [20, 21], [30, 30],
+                    [30, 31], [31, 30]], float)
+    D = np.linalg.norm(n12[:, None] - n12[None], axis=-1)
+    c = oknn.heap_knn(lambda i, j: D[i, j], 12, 5)
+    adj = oknn.greedy_degree(c, lambda i, j: True, 3)
+    assert [len(a) for a in adj] == list(g["n12_degree_deg"])
+    assert sum(adj, []) == list(g["n12_degree_adj"])
+    # production method output on the 12-node case
+    assert adj[4] == [5, 6] and adj[8] == [7, 9, 5] and adj[11] == [10]
+    qs = g["samples"]
+    for metric in ("l2", "fk"):
+        if metric == "l2":
+            Dm = np.sqrt(((qs[:, None] - qs[None]) ** 2).sum(-1))
+        else:
+            Dm = np.stack([chain.panda_pose_distance(np.repeat(qs[i:i + 1], len(qs), 0), qs) for i in range(len(qs))])
+        idx, dist = oknn.brute_knn(Dm, 10)
+        ref_idx, ref_d = g[f"{metric}_knn_idx"], g[f"{metric}_knn_dist"]
+        bad = idx != ref_idx
+        # only float64 last-bit ties may differ
+        assert bad.mean() < 0.01
+        assert np.abs(dist - ref_d).max() < 1e-9
+
+
+def test_scipy_fixture_knn(golden):
+    # reference fixtures res/images/{random,halton}_{samples,degree_roadmap}.csv (k=5)
+    g = golden("scipy_knn")
+    for name in ("random", "halton"):
+        s = g[name + "_samples"]
+        D = np.sqrt(((s[:, None] - s[None]) ** 2).sum(-1))
+        idx, _ = oknn.brute_knn(D, 5)
+        pairs = np.stack([np.repeat(np.arange(len(s)), 5), idx.ravel()], 1)
+        assert (pairs == g[name + "_degree"]).all()
+        # radius 0.2 fixture: same SET of directed pairs (cKDTree order inside a ball is unspecified)
+        got = {(i, j) for i in range(len(s)) for j in range(len(s)) if i != j and D[i, j] <= 0.2}
+        assert got == {tuple(p) for p in g[name + "_distance"]}
+
+
+def test_philox_known_answer_and_rounding():
+    # Random123 known-answer test vector for philox4x32-10 (counter = key = 0)
+    r = sampling.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = sampling.philox4x32_10([0xffffffff], [0xffffffff], [0xffffffff], [0xffffffff], 0xffffffff, 0xffffffff)
+    assert [int(x[0]) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    s = sampling.sample_uniform([-1, 0], [1, 3], 1000, seed=7)
+    assert ((s >= [-1, 0]) & (s <= [1, 3])).all()
+    assert np.abs(s * 100 - np.rint(s * 100)).max() < 1e-9
+    assert (s == np.round(s, 2)).all()
+
+
+def test_hull_oracle_known_answers():
+    from oracle import hull
+    s = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], float)
+    assert hull.distance(s, s + [3, 0, 0]) == pytest.approx(2.0)
+    assert hull.distance(s, s + [1.5, 1.5, 0]) == pytest.approx(np.sqrt(0.5))
+    assert hull.distance(s, s + [2, 2, 2]) == pytest.approx(np.sqrt(3.0))
+    assert hull.distance(s, s + [0.5, 0.5, 0.5]) == 0.0
+    assert hull.distance(s, s + [1, 0, 0]) == 0.0          # touching = collision (distance <= 0)
+    assert hull.distance(s[:1], s[:1] + [0, 0, 5], 1.0, 1.5) == pytest.approx(2.5)   # two spheres
+    rng = np.random.default_rng(0)
+    for _ in range(50):   # random tetrahedra vs brute-force sampled distance upper bound
+        a, b = rng.normal(size=(4, 3)), rng.normal(size=(4, 3)) + [4, 0, 0]
+        d = hull.distance(a, b)
+        w = rng.dirichlet(np.ones(4), size=(2, 4000))
+        ub = np.linalg.norm((w[0] @ a)[:, None] - (w[1] @ b)[None], axis=-1).min()
+        assert d <= ub + 1e-9 and d > ub - 0.25
