@@ -159,10 +159,12 @@ int mmmp_fk_chain(const mmmp_world* w, int robot, const float* q_d, int ld, int6
 /* feature rows of the FK metric: out_d [N, ldf] fp32 = xyz of the selected
  * frames (frames_h[g] in 1..n_joints+1, the tip being n_joints+1), zero padded.
  * Panda.task_space_pose_distance (robots/panda.py:248-254) only depends on
- * frames 3,4,5(=6),7,8 -> 5 groups with weights 1,1,2,1,1.                  */
+ * frames 3,4,5(=6),7,8 -> 5 groups with weights 1,1,2,1,1.
+ * out_filter_d (may be NULL) [N, 4] = (sum_g w_g p_g, 0): the filter row of the
+ * neighbour scan (sum_g w_g |dp_g| >= |sum_g w_g dp_g|), 16-byte aligned.       */
 int mmmp_fk_features(const mmmp_world* w, int robot, const float* q_d, int ld, int64_t N,
-                     const int32_t* frames_h, int n_frames, float* out_d, int ldf,
-                     void* stream);
+                     const int32_t* frames_h, const float* weights_h, int n_frames,
+                     float* out_d, int ldf, float* out_filter_d, void* stream);
 /* frame groups of the FK metric for mmmp_fk_features / mmmp_metric: frames whose
  * origin depends on q, coincident consecutive frames merged with multiplicity as
  * weight.  frames_h / weights_h hold MMMP_MAX_GROUPS entries.                 */
@@ -241,10 +243,24 @@ typedef struct mmmp_metric {
  * id in [id_lo, id_hi_i) excluding the query's own id when exclude_self;
  * id_hi_i = min(n_ref, causal ? query id : n_ref)  (causal = only earlier
  * nodes, the incremental planners).  Output ascending (dist, id); missing
- * slots get id -1 and dist +inf.  out_dist_d may be NULL.                   */
-int mmmp_knn(const float* ref_d, int64_t n_ref, const float* query_d, int64_t n_query,
-             int ldf, const mmmp_metric* metric_h, int k, int exclude_self, int causal,
-             int64_t query_id0, int32_t* out_idx_d, float* out_dist_d, void* stream);
+ * slots get id -1 and dist +inf.  out_dist_d may be NULL.
+ * Two row sets per side: FILTER rows fref_d/fquery_d [., ldf] whose first fdim
+ * (<= 31) columns have a plain L2 distance that is a LOWER BOUND of the metric
+ * -- every pair is tested against it in the hot loop -- and EXACT rows
+ * xref_d/xquery_d [., ldx] on which metric_h is evaluated for the pairs that
+ * pass.  L2 / SQ_SUM: pass the same rows for both (fdim = metric.dim).
+ * GROUP_L2_SUM: exact rows = mmmp_fk_features out_d, filter rows = its
+ * out_filter_d (ldf 4, fdim 3).  n_ref < 2^28.                              */
+int mmmp_knn(const float* fref_d, const float* xref_d, int64_t n_ref,
+             const float* fquery_d, const float* xquery_d, int64_t n_query,
+             int ldf, int fdim, int ldx, const mmmp_metric* metric_h, int k,
+             int exclude_self, int causal, int64_t query_id0, int32_t* out_idx_d,
+             float* out_dist_d, void* stream);
+
+/* profiling aid: enable != 0 turns on two device counters of the scan kernel
+ * (rare-path entries, list insertions); out2_h (may be NULL) receives and
+ * resets them; enable == 0 frees them.                                       */
+int mmmp_knn_stats(int enable, unsigned long long* out2_h);
 
 /* Re-rank candidates in fp64 with the reference's own arithmetic order:
  * cand_idx_d [n_query, kc] (from mmmp_knn with kc >= k) -> out [n_query, k]

@@ -101,7 +101,7 @@ SIGNATURES = {
     "mmmp_sample_uniform": [_P, _P, _I, _I64, _U64, _U64, _I, _P, _I, _P, _I, _P],
     "mmmp_pack_f32": [_P, _I, _I, _I64, _P, _I, _P],
     "mmmp_fk_chain": [_P, _I, _P, _I, _I64, _P, _P, _P],
-    "mmmp_fk_features": [_P, _I, _P, _I, _I64, _P, _I, _P, _I, _P],
+    "mmmp_fk_features": [_P, _I, _P, _I, _I64, _P, _P, _I, _P, _I, _P, _P],
     "mmmp_fk_metric_groups": [_P, _I, _P, _P, _P],
     "mmmp_fk_chain_f64": [_P, _I, _P, _I, _I64, _P, _P],
     "mmmp_planar_fk": [_P, _I, _P, _I, _I64, _P, _P],
@@ -111,7 +111,8 @@ SIGNATURES = {
     "mmmp_collide_robot_pairs": [_P, _I, _I, _P, _P, _I, _I64, _P, _P],
     "mmmp_compact_free": [_P, _I64, _P, _P, _P],
     "mmmp_gather_rows": [_P, _I, _P, _I64, _P, _P],
-    "mmmp_knn": [_P, _I64, _P, _I64, _I, C.POINTER(Metric), _I, _I, _I, _I64, _P, _P, _P],
+    "mmmp_knn": [_P, _P, _I64, _P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _I, _I64, _P, _P, _P],
+    "mmmp_knn_stats": [_I, _P],
     "mmmp_knn_refine": [_P, _P, _I, C.POINTER(Metric), _P, _P, _I64, _I, _I, _D, _P, _P, _P, _P],
     "mmmp_radius": [_P, _P, _I64, _P, _P, _I64, _I, _I, C.POINTER(Metric), C.POINTER(Metric), _D, _I, _I, _I, _I,
                     _I64, _P, _P, _P, _P, _P],

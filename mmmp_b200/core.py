@@ -194,7 +194,12 @@ def _dev(t: torch.Tensor, dtype) -> torch.Tensor:
 
 
 def pad4(d: int) -> int:
-    return (d + 3) & ~3
+    """Row width of fp32 configuration / feature rows: 4, 8, 16 or 32 floats (the widths the
+    neighbour-search kernels are instantiated for)."""
+    for w in (4, 8, 16, 32):
+        if d <= w:
+            return w
+    raise MmmpError(f"row of {d} floats is wider than 32")
 
 
 def to_device_f64(a) -> torch.Tensor:
@@ -262,15 +267,52 @@ def make_metric(kind: int, dim: int, weights: Sequence[float] = ()) -> Metric:
     return m
 
 
-def knn(ref: torch.Tensor, query: torch.Tensor, metric: Metric, k: int, exclude_self: bool = True,
-        causal: bool = False, query_id0: int = 0):
+@dataclass
+class Features:
+    """Row sets of one point set for neighbour search.
+    filt: fp32 filter rows [n, 4|8|16|32] whose L2 distance lower-bounds the metric;
+    x32 : fp32 exact rows the fp32 metric (m32) is evaluated on;
+    x64 : fp64 rows the float64 re-rank metric (m64) is evaluated on."""
+    filt: torch.Tensor
+    x32: torch.Tensor
+    x64: torch.Tensor
+    m32: Metric
+    m64: Metric
+    fdim: int = 0            # filter columns used (0 = m32.dim)
+
+    def rows(self, lo: int, hi: int) -> "Features":
+        return Features(self.filt[lo:hi], self.x32[lo:hi], self.x64[lo:hi], self.m32, self.m64, self.fdim)
+
+    def __len__(self):
+        return self.x32.shape[0]
+
+
+def l2_features(q64: torch.Tensor, q32: Optional[torch.Tensor] = None, squared: bool = False) -> Features:
+    """np.linalg.norm(q1 - q2) on configuration rows (decoupled_prm.py:824, coupled_prm.py:131);
+    squared=True gives sum of squares on the rows (planar_arm.py:54-61 on stacked link positions,
+    then m64 groups the columns in pairs)."""
+    q64 = _dev(q64, torch.float64)
+    q32 = pack_f32(q64) if q32 is None else _dev(q32, torch.float32)
+    D = q64.shape[1]
+    if squared:
+        m32 = make_metric(METRIC_SQ_SUM, D)
+        m64 = make_metric(METRIC_SQ_SUM, D, [1.0] * (D // 2))
+    else:
+        m32 = m64 = make_metric(METRIC_L2, D)
+    return Features(q32, q32, q64, m32, m64)
+
+
+def knn(ref: Features, query: Features, k: int, exclude_self: bool = True, causal: bool = False,
+        query_id0: int = 0):
     """fp32 scan -> (idx [nq, k] int32, dist [nq, k] fp32), ascending (dist, id)."""
-    ref, query = _dev(ref, torch.float32), _dev(query, torch.float32)
-    nq, ldf = query.shape
-    idx = torch.empty((nq, k), dtype=torch.int32, device=ref.device)
-    dist = torch.empty((nq, k), dtype=torch.float32, device=ref.device)
-    _lib.call("mmmp_knn", _ptr(ref), ref.shape[0], _ptr(query), nq, ldf, C.byref(metric), k, int(exclude_self),
-              int(causal), query_id0, _ptr(idx), _ptr(dist), _stream())
+    fr, fq = _dev(ref.filt, torch.float32), _dev(query.filt, torch.float32)
+    xr, xq = _dev(ref.x32, torch.float32), _dev(query.x32, torch.float32)
+    nq = fq.shape[0]
+    idx = torch.empty((nq, k), dtype=torch.int32, device=fr.device)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=fr.device)
+    fdim = ref.fdim or ref.m32.dim
+    _lib.call("mmmp_knn", _ptr(fr), _ptr(xr), fr.shape[0], _ptr(fq), _ptr(xq), nq, fr.shape[1], fdim, xr.shape[1],
+              C.byref(ref.m32), k, int(exclude_self), int(causal), query_id0, _ptr(idx), _ptr(dist), _stream())
     return idx, dist
 
 
@@ -288,25 +330,24 @@ def knn_refine(ref64: torch.Tensor, query64: torch.Tensor, metric64: Metric, can
     return idx, dist, amb
 
 
-def knn_exact(ref32, ref64, query32, query64, metric32: Metric, metric64: Metric, k: int, pad: int = 6,
-              exclude_self: bool = True, causal: bool = False, query_id0: int = 0):
-    """scan with k+pad candidates, then fp64 re-rank."""
+def knn_exact(ref: Features, query: Features, k: int, pad: int = 6, exclude_self: bool = True,
+              causal: bool = False, query_id0: int = 0):
+    """scan with k+pad candidates, then fp64 re-rank -> (idx, dist64, ambiguous)."""
     kc = min(k + pad, _lib.MAX_K)
-    ci, cd = knn(ref32, query32, metric32, kc, exclude_self, causal, query_id0)
-    return knn_refine(ref64, query64, metric64, ci, cd, k)
+    ci, cd = knn(ref, query, kc, exclude_self, causal, query_id0)
+    return knn_refine(ref.x64, query.x64, ref.m64, ci, cd, k)
 
 
-def radius_search(ref32, ref64, query32, query64, metric32: Metric, metric64: Metric, r: float,
-                  strict: bool = False, exclude_self: bool = True, exclude_zero: bool = False,
-                  causal: bool = False, query_id0: int = 0):
+def radius_search(ref: Features, query: Features, r: float, strict: bool = False, exclude_self: bool = True,
+                  exclude_zero: bool = False, causal: bool = False, query_id0: int = 0):
     """CSR neighbour lists within r: (offsets [nq+1] int64, idx int32, dist fp64); ids ascending per row."""
-    ref32, query32 = _dev(ref32, torch.float32), _dev(query32, torch.float32)
-    ref64, query64 = _dev(ref64, torch.float64), _dev(query64, torch.float64)
+    ref32, query32 = _dev(ref.x32, torch.float32), _dev(query.x32, torch.float32)
+    ref64, query64 = _dev(ref.x64, torch.float64), _dev(query.x64, torch.float64)
     nq, ldf = query32.shape
     counts = torch.zeros((nq,), dtype=torch.int32, device=ref32.device)
     args = lambda cnt, off, oi, od: (  # noqa: E731
         _ptr(ref32), _ptr(ref64), ref32.shape[0], _ptr(query32), _ptr(query64), nq, ldf, ref64.shape[1],
-        C.byref(metric32), C.byref(metric64), C.c_double(r), int(strict), int(exclude_self), int(exclude_zero),
+        C.byref(ref.m32), C.byref(ref.m64), C.c_double(r), int(strict), int(exclude_self), int(exclude_zero),
         int(causal), query_id0, _ptr(cnt), _ptr(off), _ptr(oi), _ptr(od), _stream())
     _lib.call("mmmp_radius", *args(counts, None, None, None))
     offsets = exclusive_scan(counts)
@@ -437,19 +478,26 @@ class SpatialWorld(_World):
         _lib.call("mmmp_fk_metric_groups", self.handle, robot, frames, weights, C.byref(n))
         return list(frames[: n.value]), list(weights[: n.value])
 
-    def fk_features(self, q32: torch.Tensor, robot: int = 0):
-        """fp32 feature rows of the FK metric and the matching (metric32, metric64)."""
-        q32 = _dev(q32, torch.float32)
+    def fk_features(self, q64: torch.Tensor, q32: Optional[torch.Tensor] = None, robot: int = 0) -> Features:
+        """Row sets of the FK metric (Panda.task_space_pose_distance, robots/panda.py:248-254):
+        exact fp32 rows = xyz of the q-dependent frames (coincident frames merged, weights =
+        multiplicity), filter rows = their weighted centroid, fp64 rows = all frame positions."""
+        q64 = _dev(q64, torch.float64)
+        q32 = pack_f32(q64) if q32 is None else _dev(q32, torch.float32)
         frames, weights = self.metric_groups(robot)
         ldf = pad4(3 * len(frames))
-        out = torch.empty((q32.shape[0], ldf), dtype=torch.float32, device=q32.device)
+        n = q32.shape[0]
+        out = torch.empty((n, ldf), dtype=torch.float32, device=q32.device)
+        filt = torch.empty((n, 4), dtype=torch.float32, device=q32.device)
         fr = (C.c_int32 * len(frames))(*frames)
-        _lib.call("mmmp_fk_features", self.handle, robot, _ptr(q32), q32.shape[1], q32.shape[0], fr, len(frames),
-                  _ptr(out), ldf, _stream())
+        wt = (C.c_float * len(frames))(*weights)
+        _lib.call("mmmp_fk_features", self.handle, robot, _ptr(q32), q32.shape[1], n, fr, wt, len(frames),
+                  _ptr(out), ldf, _ptr(filt), _stream())
         L = self.robots[robot].model["n_joints"] + 1
+        pos64 = self.fk64(q64, robot).reshape(n, 3 * L)
         m32 = make_metric(METRIC_GROUP_L2_SUM, 3 * len(frames), weights)
         m64 = make_metric(METRIC_GROUP_L2_SUM, 3 * L, [1.0] * L)
-        return out, m32, m64
+        return Features(filt, out, pos64, m32, m64, 3)
 
     def collide_robot_pairs(self, qa: torch.Tensor, qb: torch.Tensor, ra: int, rb: int):
         qa, qb = _dev(qa, torch.float32), _dev(qb, torch.float32)

@@ -63,12 +63,14 @@ fk_chain_kernel(const WorldDev* __restrict__ W, int robot, const float* __restri
 struct FrameSel {
     int n;
     int frame[MMMP_MAX_GROUPS];  // 1-based frame numbers (tip = n_joints + 1)
+    float weight[MMMP_MAX_GROUPS];
 };
 
-// FK-metric feature rows: xyz of the selected frames, zero padded to ldf
+// FK-metric feature rows: xyz of the selected frames, zero padded to ldf; and the filter
+// row of the neighbour scan: the weighted centroid sum_g w_g p_g (xyz, 0)
 __global__ void __launch_bounds__(256)
 fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __restrict__ q, int ld, int64_t N,
-                   FrameSel sel, float* __restrict__ out, int ldf) {
+                   FrameSel sel, float* __restrict__ out, int ldf, float4* __restrict__ out_filter) {
     __shared__ ChainSmem C;
     {
         const RobotDev& R = W->robots[robot];
@@ -84,6 +86,7 @@ fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __res
         affine_load(T, C.base);
         const float* qi = q + i * ld;
         float* o = out + i * ldf;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
         for (int j = 0; j <= n; ++j) {
             if (j < n) {
                 float s, c;
@@ -97,9 +100,13 @@ fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __res
                     o[3 * g + 0] = T.m[3];
                     o[3 * g + 1] = T.m[7];
                     o[3 * g + 2] = T.m[11];
+                    cx = fmaf(sel.weight[g], T.m[3], cx);
+                    cy = fmaf(sel.weight[g], T.m[7], cy);
+                    cz = fmaf(sel.weight[g], T.m[11], cz);
                 }
         }
         for (int c = 3 * sel.n; c < ldf; ++c) o[c] = 0.f;
+        if (out_filter) out_filter[i] = make_float4(cx, cy, cz, 0.f);
     }
 }
 
@@ -183,20 +190,27 @@ extern "C" int mmmp_fk_chain_f64(const mmmp_world* w, int robot, const double* q
 }
 
 extern "C" int mmmp_fk_features(const mmmp_world* w, int robot, const float* q, int ld, int64_t N,
-                                const int32_t* frames, int n_frames, float* out, int ldf, void* stream) {
+                                const int32_t* frames, const float* weights, int n_frames, float* out, int ldf,
+                                float* out_filter, void* stream) {
     if (!w || !q || !out || !frames || N < 0) return MMMP_ERR_ARG;
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
     if (n_frames < 1 || n_frames > MMMP_MAX_GROUPS || ldf < 3 * n_frames) return MMMP_ERR_ARG;
     FrameSel sel;
     sel.n = n_frames;
-    for (int g = 0; g < MMMP_MAX_GROUPS; ++g) sel.frame[g] = -1;
+    for (int g = 0; g < MMMP_MAX_GROUPS; ++g) {
+        sel.frame[g] = -1;
+        sel.weight[g] = 0.f;
+    }
     for (int g = 0; g < n_frames; ++g) {
         if (frames[g] < 1 || frames[g] > w->spatial_h->robots[robot].n_joints + 1) return MMMP_ERR_ARG;
         sel.frame[g] = frames[g];
+        sel.weight[g] = weights ? weights[g] : 1.f;
     }
+    if (out_filter && (((uintptr_t)out_filter) & 15)) return MMMP_ERR_ARG;
     if (N == 0) return MMMP_OK;
-    MMMP_LAUNCH(fk_features_kernel, fk_grid(N, 256), 256, 0, stream, w->spatial_d, robot, q, ld, N, sel, out, ldf);
+    MMMP_LAUNCH(fk_features_kernel, fk_grid(N, 256), 256, 0, stream, w->spatial_d, robot, q, ld, N, sel, out, ldf,
+                reinterpret_cast<float4*>(out_filter));
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }

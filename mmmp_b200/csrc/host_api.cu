@@ -94,7 +94,8 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
     const int nj = w->spatial_h->robots[robot].n_joints;
     if (D != nj) return MMMP_ERR_ARG;
     if (metric_kind != MMMP_METRIC_L2 && metric_kind != MMMP_METRIC_GROUP_L2_SUM) return MMMP_ERR_KIND;
-    const int ld32 = (D + 3) & ~3;
+    auto row_width = [](int d) { return d <= 4 ? 4 : (d <= 8 ? 8 : (d <= 16 ? 16 : 32)); };
+    const int ld32 = row_width(D);
     int kc = k + 6;
     if (kc > MMMP_MAX_K) kc = MMMP_MAX_K;
 
@@ -105,7 +106,7 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
     int rc = MMMP_OK;
     int64_t n_nodes = 0;
     {
-        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, pos64, cidx, cdist, ridx, rdist, edges, ecoll;
+        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, edges, ecoll;
         const int L = nj + 1;
         auto T = [&](cudaError_t e) {
             if (e != cudaSuccess && rc == MMMP_OK) rc = MMMP_ERR_CUDA_BASE + (int)e;
@@ -144,6 +145,8 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
             memset(&m32, 0, sizeof(m32));
             memset(&m64, 0, sizeof(m64));
             const float* feat_ptr = nullptr;
+            const float* filt_ptr = nullptr;
+            int ldfilt = 0;
             const double* ref64_ptr = nullptr;
             int ldf = ld32, ld64 = D;
             if (rc == MMMP_OK) {
@@ -161,7 +164,7 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                     int ng = 0;
                     R(mmmp_fk_metric_groups(w, robot, frames, wts, &ng));
                     if (rc == MMMP_OK && ng == 0) rc = MMMP_ERR_ARG;
-                    ldf = (3 * ng + 3) & ~3;
+                    ldf = row_width(3 * ng);
                     m32.kind = MMMP_METRIC_GROUP_L2_SUM;
                     m32.dim = 3 * ng;
                     m32.n_groups = ng;
@@ -173,7 +176,11 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                     T(feat.alloc(sizeof(float) * n * ldf));
                     T(pos64.alloc(sizeof(double) * n * 3 * L));
                     if (rc == MMMP_OK) {
-                        R(mmmp_fk_features(w, robot, nq32.as<float>(), ld32, n, frames, ng, feat.as<float>(), ldf, s));
+                        T(filt.alloc(sizeof(float) * n * 4));
+                        R(mmmp_fk_features(w, robot, nq32.as<float>(), ld32, n, frames, wts, ng, feat.as<float>(), ldf,
+                                           filt.as<float>(), s));
+                        filt_ptr = filt.as<float>();
+                        ldfilt = 4;
                         R(mmmp_fk_chain_f64(w, robot, nq64.as<double>(), D, n, pos64.as<double>(), s));
                     }
                     feat_ptr = feat.as<float>();
@@ -182,7 +189,13 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                 cudaEventRecord(ev[3], s);
             }
             if (rc == MMMP_OK) {
-                R(mmmp_knn(feat_ptr, n, feat_ptr, n, ldf, &m32, kc, 1, 0, 0, cidx.as<int32_t>(), cdist.as<float>(), s));
+                if (!filt_ptr) {  // L2: the rows are their own filter
+                    filt_ptr = feat_ptr;
+                    ldfilt = ldf;
+                }
+                R(mmmp_knn(filt_ptr, feat_ptr, n, filt_ptr, feat_ptr, n, ldfilt, ldfilt == 4 && filt_ptr != feat_ptr ? 3 : m32.dim,
+                           ldf, &m32, kc, 1, 0, 0,
+                           cidx.as<int32_t>(), cdist.as<float>(), s));
                 cudaEventRecord(ev[4], s);
                 R(mmmp_knn_refine(ref64_ptr, ref64_ptr, ld64, &m64, cidx.as<int32_t>(), cdist.as<float>(), n, kc, k,
                                   1e-6, ridx.as<int32_t>(), rdist.as<double>(), nullptr, s));

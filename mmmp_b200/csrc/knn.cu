@@ -95,6 +95,7 @@ __device__ __forceinline__ float filter_w2(const MetricDev& M, int col) {
     return g < M.n_groups ? M.w[g] * M.w[g] : 0.f;
 }
 
+#if 0  // superseded by knn_scan.cu
 struct KnnArgs {
     const float* ref;
     const float* query;
@@ -300,6 +301,8 @@ knn_merge_kernel(const int32_t* __restrict__ in_idx, const float* __restrict__ i
     }
 }
 
+#endif  // superseded by knn_scan.cu
+
 // ---- fp64 re-rank ------------------------------------------------------------
 // distance in the reference's arithmetic:
 //  L2            : np.linalg.norm(q1 - q2)          -> sqrt(sum_i d_i^2), i ascending
@@ -483,7 +486,8 @@ radius_kernel(RadiusArgs A) {
     if (valid && A.counts && !A.out_idx) A.counts[qi] = count;
 }
 
-int f4_for(int dim) { return dim <= 8 ? 2 : (dim <= 16 ? 4 : (dim <= 32 ? 8 : 0)); }
+// feature rows are exactly 4, 8, 16 or 32 floats wide (zero padded)
+int f4_for(int ldf) { return ldf == 4 ? 1 : (ldf == 8 ? 2 : (ldf == 16 ? 4 : (ldf == 32 ? 8 : 0))); }
 
 int fill_metric(const mmmp_metric* m, int ldf, MetricDev& M) {
     if (!m) return MMMP_ERR_ARG;
@@ -500,6 +504,7 @@ int fill_metric(const mmmp_metric* m, int ldf, MetricDev& M) {
     return MMMP_OK;
 }
 
+#if 0  // superseded by knn_scan.cu
 template <int F4, int Q>
 int launch_scan(KnnArgs& A, int n_qblocks, size_t smem, void* stream) {
     MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -508,9 +513,11 @@ int launch_scan(KnnArgs& A, int n_qblocks, size_t smem, void* stream) {
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }
+#endif
 
 }  // namespace
 
+#if 0  // superseded by knn_scan.cu
 extern "C" int mmmp_knn(const float* ref, int64_t n_ref, const float* query, int64_t n_query, int ldf,
                         const mmmp_metric* metric, int k, int exclude_self, int causal, int64_t query_id0,
                         int32_t* out_idx, float* out_dist, void* stream) {
@@ -522,7 +529,7 @@ extern "C" int mmmp_knn(const float* ref, int64_t n_ref, const float* query, int
     if (rc) return rc;
     if (n_query == 0) return MMMP_OK;
     const int F4 = f4_for(ldf);
-    if (!F4) return MMMP_ERR_LIMIT;
+    if (!F4) return MMMP_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int dev = 0, sms = 148;
     MMMP_CUDA_TRY(cudaGetDevice(&dev));
@@ -558,7 +565,9 @@ extern "C" int mmmp_knn(const float* ref, int64_t n_ref, const float* query, int
     A.out_val = tmp_val;
     const size_t smem = (size_t)KNN_STAGES * KNN_TILE * ldf * 4 + (size_t)KNN_STAGES * KNN_TILE * 4 +
                         (size_t)k * KNN_THREADS * Q * 8 + KNN_STAGES * 8 + 16;
-    if (F4 == 2 && Q == 2) rc = launch_scan<2, 2>(A, n_qblocks, smem, stream);
+    if (F4 == 1 && Q == 2) rc = launch_scan<1, 2>(A, n_qblocks, smem, stream);
+    else if (F4 == 1) rc = launch_scan<1, 1>(A, n_qblocks, smem, stream);
+    else if (F4 == 2 && Q == 2) rc = launch_scan<2, 2>(A, n_qblocks, smem, stream);
     else if (F4 == 2) rc = launch_scan<2, 1>(A, n_qblocks, smem, stream);
     else if (F4 == 4 && Q == 2) rc = launch_scan<4, 2>(A, n_qblocks, smem, stream);
     else if (F4 == 4) rc = launch_scan<4, 1>(A, n_qblocks, smem, stream);
@@ -575,6 +584,8 @@ extern "C" int mmmp_knn(const float* ref, int64_t n_ref, const float* query, int
     cudaFreeAsync(tmp_val, s);
     return rc;
 }
+
+#endif
 
 extern "C" int mmmp_knn_refine(const double* ref64, const double* query64, int ld64, const mmmp_metric* metric,
                                const int32_t* cand_idx, const float* cand_dist, int64_t n_query, int kc, int k,
@@ -632,7 +643,8 @@ extern "C" int mmmp_radius(const float* ref, const double* ref64, int64_t n_ref,
     A.out_dist = out_dist;
     const size_t smem = (size_t)KNN_TILE * ldf * 4 + KNN_TILE * 4;
     const int grid = mmmp_div_up(n_query, KNN_THREADS);
-    if (F4 == 2) MMMP_LAUNCH((radius_kernel<2>), grid, KNN_THREADS, smem, stream, A);
+    if (F4 == 1) MMMP_LAUNCH((radius_kernel<1>), grid, KNN_THREADS, smem, stream, A);
+    else if (F4 == 2) MMMP_LAUNCH((radius_kernel<2>), grid, KNN_THREADS, smem, stream, A);
     else if (F4 == 4) MMMP_LAUNCH((radius_kernel<4>), grid, KNN_THREADS, smem, stream, A);
     else MMMP_LAUNCH((radius_kernel<8>), grid, KNN_THREADS, smem, stream, A);
     MMMP_LAUNCH_CHECK();

@@ -1,0 +1,150 @@
+"""Device-resident roadmap construction pipeline (one arm), optionally sharded over the
+ranks of a torch.distributed process group (one process per GPU, NCCL over NVLink).
+
+Reference path replaced (planners/prm/pybullet/decoupled/decoupled_prm.py):
+  sample_valid_in_joint_space_random :310-321  -> sample_free()
+  connect_nearest_neighbors_degree   :480-504  -> candidates() (+ host greedy replay)
+  is_collision_free_sample / _edge   :840-863  -> collision kernels
+
+Sharding: rank g draws and checks a contiguous block of candidate
+samples; the collision-free rows are all-gathered in rank order, which reproduces the
+single-GPU node order exactly; every rank then owns the contiguous query rows
+[g*n/G, (g+1)*n/G) for neighbour search and edge checks against the full gathered
+set, and the per-row results are all-gathered.  No other collective is needed.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import core
+from ._lib import CHECK_OBSTACLES, CHECK_SELF, METRIC_GROUP_L2_SUM, METRIC_L2
+
+
+class PhaseTimer:
+    """CUDA-event timer on the current stream; phases accumulate across calls."""
+
+    def __init__(self):
+        self.events = []
+        self.totals = {}
+
+    def mark(self, name: str):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.events.append((name, e))
+
+    def collect(self):
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(self.events[:-1], self.events[1:]):
+            if n1 is None:
+                continue
+            self.totals[n1] = self.totals.get(n1, 0.0) + e0.elapsed_time(e1)
+        self.events = []
+        return self.totals
+
+
+class RoadmapBuilder:
+    def __init__(self, world: core.SpatialWorld, robot: int = 0, metric: str = "fk", k: int = 10,
+                 n_steps: int = 50, step: float = 0.02, flags: int = CHECK_SELF | CHECK_OBSTACLES,
+                 group=None, timer: Optional[PhaseTimer] = None, knn_pad: int = 6):
+        self.world, self.robot, self.metric, self.k = world, robot, metric, k
+        self.n_steps, self.step, self.flags, self.knn_pad = n_steps, step, flags, knn_pad
+        self.group = group
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.rank = torch.distributed.get_rank(group)
+            self.size = torch.distributed.get_world_size(group)
+        else:
+            self.rank, self.size = 0, 1
+        self.timer = timer
+        lim = np.array(world.robots[robot].model["joint_limits"], dtype=np.float64)
+        self.lo, self.hi = lim[:, 0].copy(), lim[:, 1].copy()
+        self.D = lim.shape[0]
+        self.accept_rate = None
+
+    def _mark(self, name):
+        if self.timer is not None:
+            self.timer.mark(name)
+
+    # ------------------------------------------------------------------ collectives
+    def _all_gather_rows(self, t: torch.Tensor, counts=None) -> torch.Tensor:
+        """Concatenate per-rank row blocks in rank order (rows may differ per rank)."""
+        if self.size == 1:
+            return t
+        import torch.distributed as dist
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        ns = torch.empty((self.size,), dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(ns, n, group=self.group)
+        ns = ns.tolist()
+        m = max(ns)
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        out = torch.empty((self.size * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        if all(x == m for x in ns):
+            return out
+        return torch.cat([out[g * m: g * m + ns[g]] for g in range(self.size)], 0)
+
+    # ------------------------------------------------------------------ sampling
+    def sample_free(self, n: int, seed: int, oversample: float = 1.05, first_index: int = 0):
+        """n collision-free joint-space samples (ids = acceptance order of the global
+        candidate stream), identical on every rank.  -> (q64 [n, D], q32 [n, ld])"""
+        rate = self.accept_rate or 0.5
+        got64, got32, have = [], [], 0
+        first = first_index
+        while have < n:
+            m = int(np.ceil((n - have) / rate * oversample)) + 64
+            m = ((m + self.size - 1) // self.size) * self.size
+            per = m // self.size
+            q64, q32 = core.sample_uniform(self.lo, self.hi, per, seed, first + self.rank * per)
+            hit = self.world.collide_configs(q32, self.robot, self.flags)
+            idx = core.compact_free(hit)
+            f64 = core.gather_rows(q64, idx)
+            f64 = self._all_gather_rows(f64)
+            rate = max(f64.shape[0] / m, 1e-3)
+            got64.append(f64)
+            have += f64.shape[0]
+            first += m
+        self.accept_rate = rate
+        q64 = (got64[0] if len(got64) == 1 else torch.cat(got64, 0))[:n].contiguous()
+        q32 = core.pack_f32(q64)
+        self._mark("sample+config_collision")
+        return q64, q32
+
+    # ------------------------------------------------------------------ neighbour search + edges
+    def features(self, q64: torch.Tensor, q32: torch.Tensor) -> core.Features:
+        if self.metric == "l2":
+            return core.l2_features(q64, q32)
+        return self.world.fk_features(q64, q32, self.robot)
+
+    def candidates(self, q64: torch.Tensor, q32: torch.Tensor, gather: bool = True):
+        """k nearest candidates of every node + the verdict of every candidate edge.
+        -> dict(idx [n,k] int32, dist [n,k] fp64, edge_free [n,k] uint8, ambiguous [n] uint8)"""
+        n = q64.shape[0]
+        per = (n + self.size - 1) // self.size
+        lo, hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
+        feats = self.features(q64, q32)
+        mine = feats.rows(lo, hi)
+        self._mark("features")
+        kc = min(self.k + self.knn_pad, 64)
+        ci, cd = core.knn(feats, mine, kc, exclude_self=True, causal=False, query_id0=lo)
+        self._mark("knn_scan")
+        idx, dist, amb = core.knn_refine(feats.x64, mine.x64, feats.m64, ci, cd, self.k)
+        self._mark("knn_rerank")
+        edges = core.edges_from_knn(idx)
+        if lo > 0:
+            edges[:, 0] += lo
+        hit = self.world.collide_edges(q32, edges, self.n_steps, self.step, self.robot, self.flags)
+        free = (hit == 0).to(torch.uint8).reshape(hi - lo, self.k)
+        self._mark("edge_collision")
+        if gather and self.size > 1:
+            idx, dist, free, amb = (self._all_gather_rows(t) for t in (idx, dist, free, amb))
+            self._mark("gather_adjacency")
+        return {"idx": idx, "dist": dist, "edge_free": free, "ambiguous": amb, "rows": (lo, hi)}
+
+    def build(self, n: int, seed: int):
+        q64, q32 = self.sample_free(n, seed)
+        out = self.candidates(q64, q32)
+        out["q64"], out["q32"] = q64, q32
+        return out
