@@ -444,9 +444,10 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     // queries per thread: as many as keep every SM busy with >= 2 CTAs of work
+    // (measured on B200: Q = 2 beats 4 and 8 for every row width -- more resident warps win)
     const int qmax = F4 <= 1 ? 8 : (F4 <= 2 ? 4 : (F4 <= 4 ? 2 : 1));
     int Q = 1;
-    while (Q < qmax && n_query >= (int64_t)sms * KNN_CTHREADS * (2 * Q) * 2) Q *= 2;
+    if (qmax >= 2 && n_query >= (int64_t)sms * KNN_CTHREADS * 2 * 2) Q = 2;
     if (const char* e = getenv("MMMP_KNN_Q")) {
         const int q = atoi(e);
         if ((q == 1 || q == 2 || q == 4 || q == 8) && q <= qmax) Q = q;

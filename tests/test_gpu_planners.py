@@ -1,0 +1,278 @@
+"""GPU parity tests of the planner layer (the reference's plugin API for the hot path):
+roadmaps built by the mmmp_b200 planner classes from FIXED samples must equal, list by list,
+the roadmaps the reference's own classes built from the same samples
+(tests/golden/planar_roadmaps.npz, panda_heap_knn.npz -- written by tools/gen_golden.py from
+the reference itself), and planned CBS-PRM paths must be collision free under the hull
+oracle (the restatement of the reference checker)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LIMITS = np.array([(-2.8973, 2.8973), (-1.7628, 1.7628), (-2.8973, 2.8973), (-3.0718, -0.0698),
+                   (-2.8973, 2.8973), (-0.0175, 3.7525), (-2.8973, 2.8973)])
+
+
+def _adj(roadmap, n):
+    deg = np.array([len(roadmap[i]) for i in range(n)])
+    flat = np.concatenate([np.array(roadmap[i], dtype=np.int64) for i in range(n)] + [np.zeros(0, np.int64)])
+    return deg, flat
+
+
+@pytest.fixture(scope="module")
+def planar_envs(cuda, golden):
+    from mmmp_b200.planners.prm.planar.env import Environment
+    from mmmp_b200.robots.planar_arm import PlanarArm
+    from mmmp_b200.utils.shapes import Circle, Rectangle
+    g = golden("planar_predicates")
+    arm3 = PlanarArm(np.array([2.5, 2.0, 2.2]), np.array([0.5, -1.0]))
+    env3 = Environment((20, 20), [{"name": "a", "start": np.array([0.1, 0.2, 0.3]), "goal": np.array([0.3, 0.2, 0.1]),
+                                   "model": arm3}],
+                       [Rectangle((3.0, 1.0), 2.0, 2.0), Circle((-2.5, 2.5), 1.0)])
+    bases = g["w2_bases"]
+    arms = [PlanarArm(np.array([3.0, 3.0]), np.array(b)) for b in bases]
+    starts = [np.array([1.2, 0.4]), np.array([2.0, -0.4])]
+    agents = [{"name": f"a{i}", "start": starts[i], "goal": starts[i] + 0.3, "model": arms[i]} for i in range(2)]
+    env2 = Environment((20, 20), agents, [Rectangle((-1.5, -2.0), 3.0, 1.2), Rectangle((2.1, 3.3), 1.7, 2.9),
+                                          Circle((-3.0, 1.5), 1.1)])
+    return env3, env2
+
+
+def test_planar_environment_matches_reference_geometry(planar_envs, golden):
+    from mmmp_b200.planners.prm.planar.env import obstacle_desc
+    g = golden("planar_predicates")
+    _, env2 = planar_envs
+    rects = [obstacle_desc(o) for o in env2.obstacles if hasattr(o, "get_bbox")]
+    got = np.array([[r["x0"], r["y0"], r["x1"], r["y1"]] for r in rects])
+    assert (got == g["w2_rects"]).all()          # the bbox arithmetic of env.py:170 reproduced bit for bit
+
+
+def test_planar_single_arm_roadmaps_equal_reference(planar_envs, golden):
+    from mmmp_b200.planners.prm.planar.single_arm.degree_prm import KDTreeKNNPRM, KNNPRM
+    from mmmp_b200.planners.prm.planar.single_arm.distance_prm import DistancePRM, KDTreeDistancePRM
+    env3, _ = planar_envs
+    g = golden("planar_roadmaps")
+    samples = g["single_samples"]
+    n = len(samples)
+
+    def build(cls, **kw):
+        p = cls.__new__(cls)
+        from mmmp_b200.planners.prm.planar.single_arm.prm import PRM
+        PRM.__init__(p, env3, 0.05)
+        for k_, v_ in kw.items():
+            setattr(p, k_, v_)
+        return p
+
+    p = build(DistancePRM, max_edge_len=6.0)
+    p.add_n_samples(n, samples=samples)
+    deg, flat = _adj(p.roadmap, n)
+    assert (deg == g["distance_deg"]).all() and (flat == g["distance_adj"]).all()
+
+    p = build(KNNPRM, max_edge_len=6.0, n_knn=4)
+    p.add_n_samples(n, samples=samples)
+    deg, flat = _adj(p.roadmap, n)
+    assert (deg == g["knn_deg"]).all() and (flat == g["knn_adj"]).all()
+
+    p = build(KDTreeKNNPRM, max_edge_len=1.2, n_knn=4)
+    p.add_n_samples(n, samples=samples)
+    p.update_roadmap()
+    deg, flat = _adj(p.roadmap, n)
+    assert (deg == g["kd_knn_deg"]).all() and (flat == g["kd_knn_adj"]).all()
+
+    p = build(KDTreeDistancePRM, max_edge_len=1.2)
+    p.add_n_samples(n, samples=samples)
+    p.update_roadmap()
+    deg, flat = _adj(p.roadmap, n)
+    assert (deg == g["kd_distance_deg"]).all()
+    # cKDTree's order inside a ball is unspecified: compare the neighbour SETS per node
+    off = np.concatenate([[0], np.cumsum(deg)])
+    ref = g["kd_distance_adj"]
+    assert all(sorted(flat[off[i]:off[i + 1]]) == sorted(ref[off[i]:off[i + 1]]) for i in range(n))
+
+
+def test_planar_multi_arm_roadmaps_equal_reference(planar_envs, golden):
+    from mmmp_b200.planners.prm.planar.multi_arm.coupled.coupled_prm import CoupledPRM
+    from mmmp_b200.planners.prm.planar.multi_arm.coupled.degree_coupled_prm import KDTreeKNNCoupledPRM
+    from mmmp_b200.planners.prm.planar.multi_arm.coupled.distance_coupled_prm import DistanceCoupledPRM
+    from mmmp_b200.planners.prm.planar.multi_arm.decoupled.cbs_prm import CBSPRM
+    from mmmp_b200.planners.prm.planar.multi_arm.decoupled.decoupled_prm import DecoupledPRM
+    _, env2 = planar_envs
+    g = golden("planar_roadmaps")
+    samples = g["coupled_samples"]
+    n = len(samples)
+    p = DistanceCoupledPRM.__new__(DistanceCoupledPRM)
+    CoupledPRM.__init__(p, env2)
+    p.max_edge_len = 1.6
+    p.add_n_samples(n, samples=samples)
+    deg, flat = _adj(p.roadmap, n)
+    assert (deg == g["coupled_distance_deg"]).all() and (flat == g["coupled_distance_adj"]).all()
+
+    p = KDTreeKNNCoupledPRM.__new__(KDTreeKNNCoupledPRM)
+    CoupledPRM.__init__(p, env2)
+    p.max_edge_len, p.n_knn = 1.6, 5
+    p.add_n_samples(n, samples=samples)
+    p.update_roadmap()
+    deg, flat = _adj(p.roadmap, n)
+    assert (deg == g["coupled_kdknn_deg"]).all() and (flat == g["coupled_kdknn_adj"]).all()
+
+    s1 = g["cbs_samples_r1"]
+    p = CBSPRM.__new__(CBSPRM)
+    DecoupledPRM.__init__(p, env2)
+    p.max_edge_len = 0.9
+    p.add_n_samples(len(s1), 1, samples=s1)
+    deg, flat = _adj(p.roadmaps[1], len(s1))
+    assert (deg == g["cbs_deg_r1"]).all() and (flat == g["cbs_adj_r1"]).all()
+
+
+def test_planar_planner_builds_from_its_own_sampler(planar_envs):
+    from mmmp_b200.planners.prm.planar.multi_arm.decoupled.cbs_prm import CBSPRM
+    _, env2 = planar_envs
+    p = CBSPRM(env2, max_edge_len=1.0, build_type='n_nodes', n_nodes=300, seed=3)
+    assert p.compute_combined_nr_nodes() == 600
+    assert p.compute_combined_avg_degree() > 2.0
+    for r in (0, 1):
+        for node in p.node_lists[r][:50]:
+            assert p.is_collision_free_sample(node.q, r)
+        # symmetric adjacency
+        rm = p.roadmaps[r]
+        assert all(i in rm[j] for i in rm for j in rm[i])
+
+
+# ----------------------------------------------------------------------------- Panda
+def _panda_env(n_arms=1, obstacles=None):
+    from mmmp_b200 import core
+    from mmmp_b200.planners.prm.pybullet.env import Environment
+    from mmmp_b200.robots.panda import Panda
+    start = (0., 0., 0., round(-3 * np.pi / 4, 3), 0., round(3 * np.pi / 4, 3), round(np.pi / 4, 3))
+    goal = (0., 0., 0., round(-np.pi / 2 + np.pi / 16, 3), 0., round(np.pi / 2 - np.pi / 16, 3), round(np.pi / 4, 3))
+    if n_arms == 1:
+        pandas = [Panda(base_position=(0, 0, 0.01))]
+    else:   # sims/cbs_prm.py:27-28
+        pandas = [Panda(base_position=(0.7, 0, 0.01), base_orientation=(0, 0, 1, 0)), Panda(base_position=(-0.7, 0, 0.01))]
+    agents = [{"name": f"agent{i + 1}", "start": start, "goal": goal, "model": p} for i, p in enumerate(pandas)]
+    return Environment(agents, [core.plane((0, 0, 1), 0.0)] if obstacles is None else obstacles)
+
+
+def test_panda_robot_interface(cuda):
+    from mmmp_b200.robots.panda import Panda
+    p = Panda(base_position=(0.1, 0.2, 0.01), base_orientation=(0, 0, 1, 0))
+    assert p.arm_dimension == 7 and len(p.gripper_joints) == 2 and len(p.c_space) == 9
+    assert p.arm_c_space[3].upper == pytest.approx(-0.0698)
+    p.set_arm_pose([0.1] * 7)
+    assert p.get_arm_pose() == (0.1,) * 7
+    q_ref = [0, -np.pi / 4, 0, -3 * np.pi / 4, 0, np.pi / 2, np.pi / 4]
+    p0 = Panda()
+    assert np.allclose(p0.position_from_fk(q_ref), [0.306891, 0.0, 0.590282], atol=1e-6)
+    assert p0.task_space_pose_distance(q_ref, [.1, -.5, .2, -2, .3, 1.5, .7]) == pytest.approx(0.8277714713081394, abs=1e-12)
+    with pytest.raises(ValueError):
+        from mmmp_b200.robots.robot import Robot
+        Robot("something.sdf")
+
+
+def test_decoupled_connect_methods_equal_reference(cuda, golden):
+    """connect_nearest_neighbors_degree / _distance on the golden 300 samples with the golden edge
+    rule: edge_dicts must equal what the reference's production methods produced."""
+    from mmmp_b200.planners.prm.pybullet.decoupled.decoupled_prm import DecoupledPRM
+    g = golden("panda_heap_knn")
+    qs = g["samples"]
+    env = _panda_env(1)
+
+    class Probe(DecoupledPRM):
+        def _edges_hit(self, r_index, q32, edges):
+            e = edges.cpu().numpy()
+            q = np.array([n.q for n in self.node_lists[r_index]])
+            hit = [(int(round((q[a].sum() + q[b].sum()) * 100)) % 7) == 0 for a, b in e]   # tools/gen_golden.py ef()
+            return torch.tensor(hit, dtype=torch.uint8, device=q32.device)
+
+    p = Probe.__new__(Probe)
+    p.env, p.agents, p.robot_models, p.obstacles = env, env.agents, env.robot_models, env.obstacles
+    p.r_ids = [m.r_id for m in env.robot_models]
+    p.c_spaces = p.create_c_spaces(env.robot_models)
+    p.k1, p.k2, p.maxdist, p.local_step, p.time_step = 10, 6, 2.0, 0.02, 0.1
+    for mode in ("degree", "distance"):
+        p.node_lists, p.edge_dicts, p.node_id_q_dicts, p.node_q_id_dicts = [[]], [{}], [{}], [{}]
+        p._append_nodes(0, qs)
+        getattr(p, "connect_nearest_neighbors_" + mode)(p.r_ids[0])
+        deg, flat = _adj(p.edge_dicts[0], len(qs))
+        ref_deg, ref_flat = g[f"fk_{mode}_deg"], g[f"fk_{mode}_adj"]
+        # the only admissible differences come from float64 ties of the FK metric (< 1e-6)
+        same = (deg == ref_deg).all() and (flat == ref_flat).all()
+        if not same:
+            off_a, off_b = np.concatenate([[0], np.cumsum(deg)]), np.concatenate([[0], np.cumsum(ref_deg)])
+            diff = sum(list(flat[off_a[i]:off_a[i + 1]]) != list(ref_flat[off_b[i]:off_b[i + 1]]) for i in range(len(qs)))
+            assert diff <= 2, f"{mode}: {diff} adjacency lists differ"
+
+
+def test_load_roadmap_766(cuda, golden, tmp_path):
+    """utils/pb_data_utils.load_roadmap + DecoupledPRM.load_roadmaps on the reference's prebuilt
+    766-node Panda roadmap (golden = the reference's own parse of the CSV)."""
+    from mmmp_b200.planners.prm.pybullet.decoupled.cbsprm import CBSPRM
+    from mmmp_b200.utils.roadmap_io import load_roadmap, save_roadmap
+    g = golden("roadmap_766")
+    q, deg, adj = g["q"], g["deg"], g["adj"]
+    off = np.concatenate([[0], np.cumsum(deg)])
+    rm = {tuple(q[i]): [tuple(q[j]) for j in adj[off[i]:off[i + 1]]] for i in range(len(q))}
+    path = os.path.join(tmp_path, "roadmap.csv")
+    save_roadmap(rm, path)
+    again = load_roadmap(path)
+    assert list(again.keys()) == list(rm.keys()) and all(again[k] == rm[k] for k in rm)
+    env = _panda_env(2)
+    prm = CBSPRM(env, load_roadmap=path, maxdist=3.0, k1=55, k2=50, build_type='kdtree', prm_type='distance',
+                 n=1, t=1, time_step=0.1, local_step=0.02)
+    assert prm.compute_combined_nr_nodes() == 2 * 766
+    assert sum(len(v) for v in prm.edge_dicts[0].values()) == 4936       # 766 nodes, 4936 directed edges
+    d, f = _adj(prm.edge_dicts[1], 766)
+    assert (d == deg).all() and (f == adj).all()
+
+
+def test_cbs_prm_paths_are_collision_free_under_hull_oracle(cuda):
+    """North-star check 4: build two Panda roadmaps on the GPU, plan with CBS-PRM on the host and
+    re-validate every discretised configuration with the hull oracle (the restatement of the
+    reference's pybullet checker) -- self, ground plane and robot-robot."""
+    from mmmp_b200 import core
+    from mmmp_b200.planners.prm.pybullet.decoupled.cbsprm import CBSPRM
+    from oracle.hull import PandaHullChecker
+    env = _panda_env(2)
+    prm = CBSPRM(env, load_roadmap=None, maxdist=0.1, k1=12, k2=8, build_type='n', prm_type='degree', n=400, t=0,
+                 time_step=0.1, local_step=0.02, seed=5)
+    assert prm.compute_combined_nr_nodes() == 2 * (400 + 49)
+    for r in range(2):
+        ed = prm.edge_dicts[r]
+        assert all(i in ed[j] for i in ed for j in ed[i])
+    solution, l_t, q_t = prm.query()
+    assert solution, "CBS-PRM found no solution"
+    bases = [m.base_matrix for m in env.robot_models]
+    hull = PandaHullChecker(bases, [core.plane((0, 0, 1), 0.0)])
+    paths = {r: prm.discretize_path_in_time(r, solution[r]) for r in solution}
+    for r_index, r_id in enumerate(prm.r_ids):
+        q = np.array([np.asarray(v, float) for v in paths[r_id].values()])
+        assert not hull.config_collision(q, r_index).any()
+    # pairwise, at the reference's sweep times (cbsprm.py:165-183)
+    t_max = max(max(p.keys()) for p in paths.values())
+    qa, qb = [], []
+    for t in np.round(np.arange(0, t_max, prm.time_step), 1):
+        pa, pb = paths[prm.r_ids[0]], paths[prm.r_ids[1]]
+        qa.append(pa[min(pa.keys(), key=lambda x: abs(x - t))])
+        qb.append(pb[min(pb.keys(), key=lambda x: abs(x - t))])
+    assert not hull.robot_robot_collision(np.array(qa, float), np.array(qb, float), 0, 1).any()
+
+
+def test_coupled_panda_knn_prm(cuda):
+    from mmmp_b200.planners.prm.pybullet.coupled.degree_coupled_prm import KDTreeKNNCoupledPRM
+    from oracle.spheres import SphereChecker
+    from mmmp_b200 import core
+    env = _panda_env(2)
+    prm = KDTreeKNNCoupledPRM(env, max_edge_len=3.0, n_knn=6, n_nodes=300, seed=2)
+    assert len(prm.nodes) == 300 and len(prm.c_space) == 14
+    q = np.array([n.q for n in prm.nodes])
+    ck = SphereChecker([m.model for m in env.robot_models], [m.base_matrix for m in env.robot_models],
+                       [core.plane((0, 0, 1), 0.0)])
+    assert not ck.composite_collision(q).any()
+    # candidates are the float64 k nearest in the 14-D composite space
+    D = np.sqrt(((q[:, None] - q[None]) ** 2).sum(-1))
+    np.fill_diagonal(D, np.inf)
+    assert np.abs(np.sort(D, 1)[:, :6] - prm.last_candidates["dist"]).max() < 1e-12
+    assert all(i in prm.roadmap[j] for i in prm.roadmap for j in prm.roadmap[i])
