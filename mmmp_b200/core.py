@@ -110,8 +110,12 @@ class RobotSpec:
             frames[s["link_id"]] = s["frame"]
         for l in range(len(links)):
             d.link_frame[l] = frames.get(l, 0)
+        # link pairs PROVEN collision free over the whole joint range (tools/prove_pairs.py) are
+        # not tested at all; with use_pair_tables=False the plain sphere model is used throughout
+        proven = {tuple(p) for p in m.get("proven_free_pairs", [])} if self.use_pair_tables else set()
         for a, b in m["self_pairs"]:
-            d.self_mask[a] |= 1 << b
+            if (a, b) not in proven and (b, a) not in proven:
+                d.self_mask[a] |= 1 << b
         tables = m.get("pair_tables", []) if self.use_pair_tables else []
         d.n_pair_tables = len(tables)
         for t, pt in enumerate(tables):

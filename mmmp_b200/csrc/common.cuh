@@ -153,3 +153,18 @@ __device__ __forceinline__ float3 affine_point(const Affine& T, float x, float y
 }
 
 static inline int mmmp_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// The library's temporaries come from the device's default stream-ordered pool.  By default
+// that pool hands freed memory back to the driver at every synchronisation, which turns each
+// host sync into a multi-hundred-megabyte unmap/remap; keep the memory cached instead.
+static inline void mmmp_pool_keep(void) {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}

@@ -1,25 +1,34 @@
-// Kernel (d), scan stage: brute-force k nearest candidates in fp32 on the CUDA cores.
+// Kernel (d), scan stage: exact k nearest candidates in fp32 on the CUDA cores.
 //
-// Every (query, reference) pair is visited.  The hot loop evaluates a cheap LOWER BOUND
-// of the metric as a squared L2 distance between "filter rows" in dot-product form
+// The hot loop evaluates a cheap LOWER BOUND of the metric as a squared L2 distance
+// between "filter rows" in dot-product form
 //        s = B_r - 2 <a, r>   <=   tau_f - A_q          (B_r, A_q = squared row norms)
 // (dim FFMAs + a share of one FMNMX tree / compare per pair):
 //   L2 / SQ_SUM metrics : filter row = the row itself (the bound is the metric);
 //   FK metric sum_g w_g |dp_g| (robots/panda.py:248-254): filter row = the weighted
 //       centroid sum_g w_g p_g (3 floats) -- triangle inequality
 //       sum_g w_g |dp_g| >= | sum_g w_g dp_g |.
-// A prepare kernel packs the filter rows as [x_0 .. x_{d-1}, 0 .., B_r] (B_r in the last
-// of W = 4/8/16/32 columns), so the loop needs nothing but the row itself.
+// A pack kernel lays the filter rows out as [x_0 .. x_{d-1}, 0 .., B_r] (B_r in the last of
+// W = 4/8/16/32 columns), so the loop needs nothing but the row itself.
+//
+// Spatial ordering + exact tile culling (non-causal searches with >= 4096 references):
+// rows are counting-sorted by the Morton code of their grid cell (first three filter
+// dimensions), so that a shared-memory tile of 256 consecutive rows and a CTA's 128*Q
+// consecutive queries are both spatially compact; every tile carries its bounding box.
+// The producer walks the tiles outward from the CTA's own position and only loads a
+// tile whose box is closer to the CTA's query box than the CTA's current worst k-th
+// best bound -- a tile that is skipped cannot contain a neighbour, so the result is
+// identical to the exhaustive scan (which remains the path for causal / small searches).
 //
 // CTA = 4 consumer warps + 1 producer warp (warp specialisation).  The producer streams
-// the packed reference rows L2/HBM -> shared memory in contiguous tiles with the TMA
-// engine (cp.async.bulk, 4-stage ring, full/empty mbarriers); consumer warps never meet
-// at a CTA barrier.  Every consumer thread owns Q queries in registers and reads the
-// tile rows as shared-memory broadcasts (LDS.128), 4 rows per step.  Pairs that pass the
-// filter are appended to a small per-thread queue in shared memory; when any lane's
-// queue is nearly full the warp drains it: exact fp32 metric on the "exact rows" (read
-// from L2/HBM) and sorted insertion into the thread's candidate column, which tightens
-// the thread's threshold.
+// packed reference rows L2/HBM -> shared memory with the TMA engine (cp.async.bulk, 4-stage
+// ring, full/empty mbarriers); consumer warps never meet at a CTA barrier.  Every
+// consumer thread owns Q queries in registers and reads the tile rows as shared-memory
+// broadcasts (LDS.128), 4 rows per step, software pipelined.  Pairs that pass the filter
+// are appended to a small per-thread queue in shared memory; when any lane's queue is
+// nearly full the warp drains it: exact fp32 metric on the "exact rows" (read from
+// L2/HBM) and sorted insertion into the thread's candidate column, which tightens the
+// thread's threshold.
 //
 // Reference call sites replaced: the heap loops of
 // planners/prm/pybullet/decoupled/decoupled_prm.py:484-494,531-540,947-954 and
@@ -39,6 +48,7 @@ constexpr int KNN_RU = 4;                      // rows per inner-loop step
 constexpr int KNN_QSLACK = 16;                 // queue entries a thread may hold before its warp drains
 __host__ __device__ constexpr int knn_qcap(int Q) { return KNN_RU * Q + KNN_QSLACK; }
 constexpr float KNN_SLACK = 2.0e-5f;           // relative slack of the fp32 filter
+constexpr int KNN_CULL_MIN = 4096;             // references below which sorting does not pay
 
 struct MetricDev {
     int kind, dim, n_groups, pad;
@@ -81,13 +91,85 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
-// ---- filter-row packing -----------------------------------------------------------------
-// out[i] = [in[i][0..d), 0 .., (1 - eps) * |in[i][0..d)|^2]   (W columns)
+// ---- spatial ordering ------------------------------------------------------------------
+__device__ __forceinline__ int float_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// bbox[0..2] = min, bbox[3..5] = max of the first `nd` (<= 3) columns, as ordered ints
 __global__ void __launch_bounds__(256)
-knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, float* __restrict__ out, int W) {
+bbox_kernel(const float* __restrict__ rows, int ld, int nd, int64_t n, int* __restrict__ bbox) {
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        for (int c = 0; c < nd; ++c) {
+            const float v = rows[i * ld + c];
+            lo[c] = fminf(lo[c], v);
+            hi[c] = fmaxf(hi[c], v);
+        }
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0 && c < nd) {
+            atomicMin(bbox + c, float_ordered(lo[c]));
+            atomicMax(bbox + 3 + c, float_ordered(hi[c]));
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// Morton cell of a row (bits per axis = `bits`) in the box `bbox`
+__device__ __forceinline__ uint32_t cell_of(const float* row, int nd, const int* bbox, int bits) {
+    uint32_t key = 0;
+    const float cells = (float)(1 << bits);
+    for (int c = 0; c < nd; ++c) {
+        const float lo = ordered_float(bbox[c]), hi = ordered_float(bbox[3 + c]);
+        const float ext = hi - lo;
+        int v = ext > 0.f ? (int)((row[c] - lo) / ext * cells) : 0;
+        v = min(max(v, 0), (1 << bits) - 1);
+        key |= spread3((uint32_t)v) << c;
+    }
+    return key;
+}
+
+__global__ void __launch_bounds__(256)
+cell_hist_kernel(const float* __restrict__ rows, int ld, int nd, int64_t n, const int* __restrict__ bbox, int bits,
+                 uint32_t* __restrict__ keys, int32_t* __restrict__ hist) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float* r = in + i * ld_in;
-        float* o = out + i * W;
+        const uint32_t k = cell_of(rows + i * ld, nd, bbox, bits);
+        keys[i] = k;
+        atomicAdd(hist + k, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cell_scatter_kernel(const uint32_t* __restrict__ keys, int64_t n, const int64_t* __restrict__ offsets,
+                    int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        const int64_t pos = offsets[k] + atomicAdd(cursor + k, 1);
+        perm[pos] = (int32_t)i;
+    }
+}
+
+// ---- filter-row packing -----------------------------------------------------------------
+// out[p] = [in[perm[p]][0..d), 0 .., (1 - eps) * |.|^2]   (W columns); perm may be NULL
+__global__ void __launch_bounds__(256)
+knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, const int32_t* __restrict__ perm,
+                float* __restrict__ out, int W) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const float* r = in + (int64_t)(perm ? perm[p] : p) * ld_in;
+        float* o = out + p * W;
         float acc = 0.f;
         for (int c = 0; c < W - 1; ++c) {
             const float v = c < d ? r[c] : 0.f;
@@ -98,17 +180,48 @@ knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, float
     }
 }
 
+// per-tile bounding boxes of the packed (sorted) rows: boxes[t] = {lo0,lo1,lo2,hi0,hi1,hi2}
+__global__ void __launch_bounds__(256)
+tile_box_kernel(const float* __restrict__ packed, int W, int nd, int64_t n, float* __restrict__ boxes) {
+    const int64_t t = blockIdx.x;
+    const int64_t r = t * KNN_TILE + threadIdx.x;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    if (r < n)
+        for (int c = 0; c < nd; ++c) lo[c] = hi[c] = packed[r * W + c];
+    __shared__ float s[6][8];
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s[c][threadIdx.x >> 5] = lo[c];
+            s[3 + c][threadIdx.x >> 5] = hi[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, s[threadIdx.x][w]) : fmaxf(v, s[threadIdx.x][w]);
+        if (threadIdx.x % 3 >= nd) v = 0.f;
+        boxes[t * 6 + threadIdx.x] = v;
+    }
+}
+
 struct KnnArgs {
-    const float* pref;    // packed filter rows of the references [n_ref, W]
-    const float* pquery;  // packed filter rows of the queries [n_query, W]
-    const float* xref;    // exact rows [n_ref, ldx]
-    const float* xquery;  // exact rows [n_query, ldx]
+    const float* pref;     // packed filter rows of the references [n_ref, W] (sorted when perm != NULL)
+    const float* pquery;   // packed filter rows of the queries [n_query, W] (sorted when qperm != NULL)
+    const float* xref;     // exact rows [n_ref, ldx], original order
+    const float* xquery;   // exact rows [n_query, ldx], original order
+    const int32_t* perm;   // sorted position -> original reference row (NULL: identity)
+    const int32_t* qperm;  // sorted position -> original query row (NULL: identity)
+    const float* boxes;    // per-tile bounding boxes (NULL: no culling)
     int64_t n_ref, n_query, query_id0;
-    int ldx, kc, flags;   // flags: 1 = exclude self, 2 = causal
+    int ldx, kc, flags;    // flags: 1 = exclude self, 2 = causal
     int tiles_per_split, n_splits;
-    int32_t* out_idx;     // [n_query, n_splits, kc]
-    float* out_val;       // candidate-list domain (L2/SQ_SUM: squared ; GROUP: distance)
-    unsigned long long* stats;  // optional: [0] += exact evaluations, [1] += insertions, [2] += drains
+    int32_t* out_idx;      // [n_query, n_splits, kc]
+    float* out_val;        // candidate-list domain (L2/SQ_SUM: squared ; GROUP: distance)
+    unsigned long long* stats;  // optional: [0] exact evaluations, [1] insertions, [2] drains, [3] tiles loaded
     MetricDev M;
 };
 
@@ -130,6 +243,22 @@ __device__ __forceinline__ float exact_metric(const MetricDev& M, const float* _
     return v;
 }
 
+__device__ __forceinline__ float box_dist2(const float* a, const float* b) {  // {lo[3], hi[3]} each
+    float d2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float g = fmaxf(fmaxf(b[c] - a[3 + c], a[c] - b[3 + c]), 0.f);
+        d2 = fmaf(g, g, d2);
+    }
+    return d2;
+}
+
+struct ScanCtl {                  // per-CTA control block in shared memory
+    float wbox[KNN_CWARPS][6];    // query box of every consumer warp
+    volatile float wtau[KNN_CWARPS];  // worst (largest) filter-domain bound of every consumer warp
+    volatile int tile_id[KNN_STAGES];
+};
+
 template <int F4, int Q>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_scan_kernel(const __grid_constant__ KnnArgs A) {
@@ -137,22 +266,25 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     constexpr int W = F4 * 4;
     constexpr int LS = KNN_CTHREADS * Q;  // column stride of the per-query shared arrays
     constexpr int QCAP = knn_qcap(Q);
-    // layout: tiles[STAGES][TILE][W] | lv[kc][LS] | li[kc][LS] | queue[QCAP][CTHREADS] | full[STAGES] empty[STAGES]
+    // layout: tiles[STAGES][TILE][W] | lv[kc][LS] | li[kc][LS] | queue[QCAP][CTHREADS] | full[] empty[] | ctl
     float* tiles = reinterpret_cast<float*>(smem_raw);
     float* lv = tiles + KNN_STAGES * KNN_TILE * W;
     int* li = reinterpret_cast<int*>(lv + (size_t)A.kc * LS);
     uint32_t* queue = reinterpret_cast<uint32_t*>(li + (size_t)A.kc * LS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(queue + QCAP * KNN_CTHREADS);
+    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(bars + 2 * KNN_STAGES);
     const uint32_t tiles_s = smem_u32(tiles);
     const uint32_t full_s = smem_u32(bars), empty_s = smem_u32(bars + KNN_STAGES);
 
     const int tid = threadIdx.x;
     const int kc = A.kc;
+    const bool cull = A.boxes != nullptr;
     if (tid == 0) {
         for (int s = 0; s < KNN_STAGES; ++s) {
             mbar_init(full_s + 8 * s, 1);
             mbar_init(empty_s + 8 * s, KNN_CWARPS);
         }
+        for (int w = 0; w < KNN_CWARPS; ++w) ctl->wtau[w] = CUDART_INF_F;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -167,46 +299,119 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     const int64_t tile_lo = (int64_t)blockIdx.y * A.tiles_per_split;
     int64_t tile_hi = tile_lo + A.tiles_per_split;
     if (tile_hi > total_tiles) tile_hi = total_tiles;
-    const int n_tiles = (int)(tile_hi > tile_lo ? tile_hi - tile_lo : 0);
+
+    // ---- queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q) ----
+    float a2[Q][W - 1], thr[Q], Aq[Q], tauf[Q];
+    if (tid < KNN_CTHREADS) {
+        float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) {
+            const int64_t qi = q_first + qq * KNN_CTHREADS + tid;
+            const bool valid = qi < A.n_query;
+#pragma unroll
+            for (int i = 0; i < W - 1; ++i) {
+                const float v = valid ? __ldg(A.pquery + qi * W + i) : 0.f;
+                a2[qq][i] = -2.f * v;
+                if (i < 3 && valid) {
+                    lo[i] = fminf(lo[i], v);
+                    hi[i] = fmaxf(hi[i], v);
+                }
+            }
+            Aq[qq] = valid ? __ldg(A.pquery + qi * W + (W - 1)) : 0.f;
+            thr[qq] = valid ? CUDART_INF_F : -CUDART_INF_F;
+            tauf[qq] = valid ? CUDART_INF_F : 0.f;
+            for (int c = 0; c < kc; ++c) {
+                lv[c * LS + qq * KNN_CTHREADS + tid] = CUDART_INF_F;
+                li[c * LS + qq * KNN_CTHREADS + tid] = 0x7fffffff;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+            }
+            if ((tid & 31) == 0) {
+                ctl->wbox[tid >> 5][c] = (W - 1 > c) ? lo[c] : 0.f;
+                ctl->wbox[tid >> 5][3 + c] = (W - 1 > c) ? hi[c] : 0.f;
+            }
+        }
+    }
     __syncthreads();
 
     if (tid >= KNN_CTHREADS) {
         // ================= producer warp: one elected lane drives the TMA ring =================
         if (tid == KNN_CTHREADS) {
-            for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % KNN_STAGES;
-                mbar_wait(empty_s + 8 * s, ((t / KNN_STAGES) & 1) ^ 1);
-                const int64_t r0 = (tile_lo + t) * KNN_TILE;
-                int64_t cnt = ref_end - r0;
-                if (cnt > KNN_TILE) cnt = KNN_TILE;
-                const uint32_t bytes = (uint32_t)(cnt * W * sizeof(float));
-                mbar_expect_tx(full_s + 8 * s, bytes);
-                tma_load_1d(tiles_s + (uint32_t)s * KNN_TILE * W * 4, A.pref + r0 * W, bytes, full_s + 8 * s);
+            float cbox[6];
+            for (int c = 0; c < 3; ++c) {
+                cbox[c] = CUDART_INF_F;
+                cbox[3 + c] = -CUDART_INF_F;
+                for (int w = 0; w < KNN_CWARPS; ++w) {
+                    cbox[c] = fminf(cbox[c], ctl->wbox[w][c]);
+                    cbox[3 + c] = fmaxf(cbox[3 + c], ctl->wbox[w][3 + c]);
+                }
             }
+            int slot = 0;
+            auto push = [&](int64_t t) {  // t < 0: end marker
+                const int s = slot % KNN_STAGES;
+                mbar_wait(empty_s + 8 * s, ((slot / KNN_STAGES) & 1) ^ 1);
+                ctl->tile_id[s] = (int)t;
+                if (t < 0) {
+                    mbar_arrive(full_s + 8 * s);
+                } else {
+                    const int64_t r0 = t * KNN_TILE;
+                    int64_t cnt = ref_end - r0;
+                    if (cnt > KNN_TILE) cnt = KNN_TILE;
+                    const uint32_t bytes = (uint32_t)(cnt * W * sizeof(float));
+                    mbar_expect_tx(full_s + 8 * s, bytes);
+                    tma_load_1d(tiles_s + (uint32_t)s * KNN_TILE * W * 4, A.pref + r0 * W, bytes, full_s + 8 * s);
+                }
+                ++slot;
+            };
+            if (!cull) {
+                for (int64_t t = tile_lo; t < tile_hi; ++t) push(t);
+            } else {
+                // outward walk from the tile that holds this CTA's own rows (queries and references
+                // share the spatial order); a tile is loaded only if it can still matter
+                int64_t centre = (int64_t)((double)(q_first + LS / 2) / (double)(A.n_query > 0 ? A.n_query : 1) *
+                                           (double)total_tiles);
+                if (centre < tile_lo) centre = tile_lo;
+                if (centre >= tile_hi) centre = tile_hi - 1;
+                int64_t up = centre, down = centre - 1;
+                unsigned long long loaded = 0;
+                while (up < tile_hi || down >= tile_lo) {
+                    for (int side = 0; side < 2; ++side) {
+                        int64_t t;
+                        if (side == 0) {
+                            if (up >= tile_hi) continue;
+                            t = up++;
+                        } else {
+                            if (down < tile_lo) continue;
+                            t = down--;
+                        }
+                        float worst = 0.f;
+                        for (int w = 0; w < KNN_CWARPS; ++w) worst = fmaxf(worst, ctl->wtau[w]);
+                        const float d2 = box_dist2(cbox, A.boxes + t * 6);
+                        if (d2 > worst * (1.f + 1e-4f) + 1e-12f) continue;  // cannot hold a neighbour
+                        push(t);
+                        ++loaded;
+                    }
+                }
+                if (A.stats) atomicAdd(A.stats + 3, loaded);
+            }
+            push(-1);
         }
         return;
     }
 
     // ================= consumer warps =================
-    // queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q)
-    float a2[Q][W - 1], thr[Q], Aq[Q];
-#pragma unroll
-    for (int qq = 0; qq < Q; ++qq) {
-        const int64_t qi = q_first + qq * KNN_CTHREADS + tid;
-        const bool valid = qi < A.n_query;
-#pragma unroll
-        for (int i = 0; i < W - 1; ++i) a2[qq][i] = valid ? -2.f * __ldg(A.pquery + qi * W + i) : 0.f;
-        Aq[qq] = valid ? __ldg(A.pquery + qi * W + (W - 1)) : 0.f;
-        thr[qq] = valid ? CUDART_INF_F : -CUDART_INF_F;
-        for (int c = 0; c < kc; ++c) {
-            lv[c * LS + qq * KNN_CTHREADS + tid] = CUDART_INF_F;
-            li[c * LS + qq * KNN_CTHREADS + tid] = -1;
-        }
-    }
+    const int warp = tid >> 5;
     int qcnt = 0;
     uint32_t* myq = queue + tid;
 
     // Drain: every lane evaluates its queued (query, row) pairs exactly and inserts.
+    // Candidate order is (value, original id), so the result does not depend on visit order.
     auto drain = [&]() {
         int maxc = qcnt;
 #pragma unroll
@@ -215,118 +420,147 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             if (e < qcnt) {
                 const uint32_t ent = myq[e * KNN_CTHREADS];
                 const int qq = (int)(ent >> 28);
-                const long long id = (long long)(ent & 0x0fffffffu);
+                const long long pos = (long long)(ent & 0x0fffffffu);
                 const int col = qq * KNN_CTHREADS + tid;
-                const long long qi = q_first + col;
-                const long long qid = A.query_id0 + qi;
-                bool ok = id < ref_end;
-                if ((A.flags & 1) && id == qid) ok = false;
-                if ((A.flags & 2) && id >= qid) ok = false;
-                if (ok) {
-                    const float v = exact_metric(A.M, A.xquery + qi * A.ldx, A.xref + id * A.ldx);
-                    float* lvc = lv + col;
-                    int* lic = li + col;
-                    if (v < lvc[(kc - 1) * LS]) {
-                        int p = kc - 1;
-                        while (p > 0) {
-                            const float u = lvc[(p - 1) * LS];
-                            if (!(u > v)) break;
-                            lvc[p * LS] = u;
-                            lic[p * LS] = lic[(p - 1) * LS];
-                            --p;
-                        }
-                        lvc[p * LS] = v;
-                        lic[p * LS] = (int)id;
-                        const float tau = lvc[(kc - 1) * LS];
-                        if (tau < CUDART_INF_F) {
-                            const float tf = (A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau;
+                if (pos < ref_end) {
+                    const long long id = A.perm ? (long long)__ldg(A.perm + pos) : pos;
+                    const long long qrow = A.qperm ? (long long)__ldg(A.qperm + q_first + col) : q_first + col;
+                    const long long qid = A.query_id0 + qrow;
+                    bool ok = true;
+                    if ((A.flags & 1) && id == qid) ok = false;
+                    if ((A.flags & 2) && id >= qid) ok = false;
+                    if (ok) {
+                        const float v = exact_metric(A.M, A.xquery + qrow * A.ldx, A.xref + id * A.ldx);
+                        float* lvc = lv + col;
+                        int* lic = li + col;
+                        const float tv = lvc[(kc - 1) * LS];
+                        if (v < tv || (v == tv && (int)id < lic[(kc - 1) * LS])) {
+                            int p = kc - 1;
+                            while (p > 0) {
+                                const float u = lvc[(p - 1) * LS];
+                                const int ui = lic[(p - 1) * LS];
+                                if (!(u > v || (u == v && ui > (int)id))) break;
+                                lvc[p * LS] = u;
+                                lic[p * LS] = ui;
+                                --p;
+                            }
+                            lvc[p * LS] = v;
+                            lic[p * LS] = (int)id;
+                            const float tau = lvc[(kc - 1) * LS];
+                            if (tau < CUDART_INF_F) {
+                                const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
 #pragma unroll
-                            for (int k2 = 0; k2 < Q; ++k2)
-                                if (k2 == qq) thr[k2] = tf * (1.f + KNN_SLACK) - Aq[k2];
+                                for (int k2 = 0; k2 < Q; ++k2)
+                                    if (k2 == qq) {
+                                        thr[k2] = tf - Aq[k2];
+                                        tauf[k2] = tf;
+                                    }
+                            }
+                            if (A.stats) atomicAdd(A.stats + 1, 1ull);
                         }
-                        if (A.stats) atomicAdd(A.stats + 1, 1ull);
+                        if (A.stats) atomicAdd(A.stats, 1ull);
                     }
-                    if (A.stats) atomicAdd(A.stats, 1ull);
                 }
             }
         }
-        if (A.stats && (tid & 31) == 0) atomicAdd(A.stats + 2, 1ull);
         qcnt = 0;
+        // publish the warp's worst bound for the producer's culling test
+        float worst = 0.f;
+#pragma unroll
+        for (int k2 = 0; k2 < Q; ++k2) worst = fmaxf(worst, tauf[k2]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if ((tid & 31) == 0) {
+            ctl->wtau[warp] = worst;
+            if (A.stats) atomicAdd(A.stats + 2, 1ull);
+        }
     };
 
-    for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % KNN_STAGES;
-        const int64_t r0 = (tile_lo + t) * KNN_TILE;
+    for (int slot = 0;; ++slot) {
+        const int s = slot % KNN_STAGES;
+        mbar_wait(full_s + 8 * s, (slot / KNN_STAGES) & 1);
+        const int t = ctl->tile_id[s];
+        if (t < 0) break;
+        const int64_t r0 = (int64_t)t * KNN_TILE;
         const int cnt = (int)((ref_end - r0) < KNN_TILE ? (ref_end - r0) : KNN_TILE);
-        mbar_wait(full_s + 8 * s, (t / KNN_STAGES) & 1);
-        const uint32_t tile_s = tiles_s + (uint32_t)s * KNN_TILE * W * 4;
-        const int cnt4 = (cnt + KNN_RU - 1) & ~(KNN_RU - 1);  // stale rows of a partial tile are rejected by id
-        const uint32_t id0 = (uint32_t)r0;
-        // software pipeline: the rows of step j+1 are loaded while step j is evaluated
-        float4 rn[KNN_RU][F4];
+        bool skip = false;
+        if (cull) {  // warp-level cull: this warp's box against the tile's box
+            const float d2 = box_dist2(ctl->wbox[warp], A.boxes + (int64_t)t * 6);
+            skip = d2 > ctl->wtau[warp] * (1.f + 1e-4f) + 1e-12f;
+        }
+        if (!skip) {
+            const uint32_t tile_s = tiles_s + (uint32_t)s * KNN_TILE * W * 4;
+            const int cnt4 = (cnt + KNN_RU - 1) & ~(KNN_RU - 1);  // stale rows of a partial tile are rejected by position
+            const uint32_t id0 = (uint32_t)r0;
+            // software pipeline: the rows of step j+1 are loaded while step j is evaluated
+            float4 rn[KNN_RU][F4];
 #pragma unroll
-        for (int u = 0; u < KNN_RU; ++u)
+            for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
-            for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)(u * W + 4 * i) * 4);
+                for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)(u * W + 4 * i) * 4);
 #pragma unroll 1
-        for (int j = 0; j < cnt4; j += KNN_RU) {
-            float4 r[KNN_RU][F4];
+            for (int j = 0; j < cnt4; j += KNN_RU) {
+                float4 r[KNN_RU][F4];
 #pragma unroll
-            for (int u = 0; u < KNN_RU; ++u)
+                for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
-                for (int i = 0; i < F4; ++i) r[u][i] = rn[u][i];
-            // (the last prefetch of a tile wraps to the tile's first rows: harmless)
-            const int jn = (j + KNN_RU < KNN_TILE) ? j + KNN_RU : 0;
+                    for (int i = 0; i < F4; ++i) r[u][i] = rn[u][i];
+                const int jn = (j + KNN_RU < KNN_TILE) ? j + KNN_RU : 0;  // last prefetch wraps: harmless
 #pragma unroll
-            for (int u = 0; u < KNN_RU; ++u)
+                for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
-                for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)((jn + u) * W + 4 * i) * 4);
-            float sv[Q][KNN_RU];
-            float worst = CUDART_INF_F;  // min over queries of (best filter value - threshold)
+                    for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)((jn + u) * W + 4 * i) * 4);
+                float sv[Q][KNN_RU];
+                float worst = CUDART_INF_F;  // min over queries of (best filter value - threshold)
 #pragma unroll
-            for (int qq = 0; qq < Q; ++qq) {
+                for (int qq = 0; qq < Q; ++qq) {
 #pragma unroll
-                for (int u = 0; u < KNN_RU; ++u) {
-                    float acc = r[u][F4 - 1].w;  // B_r
+                    for (int u = 0; u < KNN_RU; ++u) {
+                        float acc = r[u][F4 - 1].w;  // B_r
 #pragma unroll
-                    for (int i = 0; i < F4; ++i) {
-                        acc = fmaf(a2[qq][4 * i + 0], r[u][i].x, acc);
-                        acc = fmaf(a2[qq][4 * i + 1], r[u][i].y, acc);
-                        acc = fmaf(a2[qq][4 * i + 2], r[u][i].z, acc);
-                        if (i < F4 - 1) acc = fmaf(a2[qq][4 * i + 3], r[u][i].w, acc);
-                    }
-                    sv[qq][u] = acc;
-                }
-                const float m = fminf(fminf(sv[qq][0], sv[qq][1]), fminf(sv[qq][2], sv[qq][3]));
-                worst = fminf(worst, m - thr[qq]);
-            }
-            // one warp-uniform branch per step; everything below it is rare
-            if (__any_sync(0xffffffffu, worst <= 0.f)) {
-#pragma unroll
-                for (int qq = 0; qq < Q; ++qq)
-#pragma unroll
-                    for (int u = 0; u < KNN_RU; ++u)
-                        if (sv[qq][u] <= thr[qq]) {
-                            myq[qcnt * KNN_CTHREADS] = ((uint32_t)qq << 28) | (id0 + (uint32_t)(j + u));
-                            ++qcnt;
+                        for (int i = 0; i < F4; ++i) {
+                            acc = fmaf(a2[qq][4 * i + 0], r[u][i].x, acc);
+                            acc = fmaf(a2[qq][4 * i + 1], r[u][i].y, acc);
+                            acc = fmaf(a2[qq][4 * i + 2], r[u][i].z, acc);
+                            if (i < F4 - 1) acc = fmaf(a2[qq][4 * i + 3], r[u][i].w, acc);
                         }
-                if (__any_sync(0xffffffffu, qcnt > KNN_QSLACK)) drain();
+                        sv[qq][u] = acc;
+                    }
+                    const float m = fminf(fminf(sv[qq][0], sv[qq][1]), fminf(sv[qq][2], sv[qq][3]));
+                    worst = fminf(worst, m - thr[qq]);
+                }
+                // one warp-uniform branch per step; everything below it is rare
+                if (__any_sync(0xffffffffu, worst <= 0.f)) {
+#pragma unroll
+                    for (int qq = 0; qq < Q; ++qq)
+#pragma unroll
+                        for (int u = 0; u < KNN_RU; ++u)
+                            if (sv[qq][u] <= thr[qq]) {
+                                myq[qcnt * KNN_CTHREADS] = ((uint32_t)qq << 28) | (id0 + (uint32_t)(j + u));
+                                ++qcnt;
+                            }
+                    if (__any_sync(0xffffffffu, qcnt > KNN_QSLACK)) drain();
+                }
             }
+            // tighten before the next culling decision
+            if (cull && __any_sync(0xffffffffu, qcnt > 0)) drain();
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty_s + 8 * s);
     }
     drain();
 
-    // ---- write the candidate columns ----------------------------------------
+    // ---- write the candidate columns (rows in ORIGINAL query order) ----------------
 #pragma unroll
     for (int qq = 0; qq < Q; ++qq) {
         const int64_t qi = q_first + qq * KNN_CTHREADS + tid;
         if (qi >= A.n_query) continue;
         const int col = qq * KNN_CTHREADS + tid;
-        const size_t o = ((size_t)qi * A.n_splits + blockIdx.y) * kc;
+        const int64_t qrow = A.qperm ? (int64_t)A.qperm[qi] : qi;
+        const size_t o = ((size_t)qrow * A.n_splits + blockIdx.y) * kc;
         for (int c = 0; c < kc; ++c) {
-            A.out_idx[o + c] = li[c * LS + col];
+            const int id = li[c * LS + col];
+            A.out_idx[o + c] = id == 0x7fffffff ? -1 : id;
             A.out_val[o + c] = lv[c * LS + col];
         }
     }
@@ -389,7 +623,7 @@ int fill_metric(const mmmp_metric* m, int ldx, MetricDev& M) {
 size_t scan_smem(int F4, int Q, int kc) {
     const size_t w = F4 * 4, ls = (size_t)KNN_CTHREADS * Q;
     return (size_t)KNN_STAGES * KNN_TILE * w * 4 + (size_t)kc * ls * 8 + (size_t)knn_qcap(Q) * KNN_CTHREADS * 4 +
-           2 * KNN_STAGES * 8 + 16;
+           2 * KNN_STAGES * 8 + sizeof(ScanCtl) + 16;
 }
 
 template <int F4, int Q>
@@ -404,17 +638,47 @@ int launch_scan(const KnnArgs& A, int n_qblocks, void* stream) {
 
 unsigned long long* g_knn_stats = nullptr;  // device counters, enabled by mmmp_knn_stats
 
+int grid_for(int64_t n, int sms) {
+    int g = mmmp_div_up(n, 256);
+    return g > sms * 16 ? sms * 16 : (g < 1 ? 1 : g);
+}
+
+// counting sort of rows by Morton cell: perm[pos] = original row
+int spatial_perm(const float* rows, int ld, int nd, int64_t n, const int* bbox_d, int bits, int32_t* perm,
+                 void* stream, int sms) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_cells = 1 << (3 * bits);
+    uint32_t* keys = nullptr;
+    int32_t* hist = nullptr;
+    int64_t* offs = nullptr;
+    MMMP_CUDA_TRY(cudaMallocAsync(&keys, sizeof(uint32_t) * n, s));
+    MMMP_CUDA_TRY(cudaMallocAsync(&hist, sizeof(int32_t) * n_cells * 2, s));
+    MMMP_CUDA_TRY(cudaMallocAsync(&offs, sizeof(int64_t) * (n_cells + 1), s));
+    MMMP_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(int32_t) * n_cells * 2, s));
+    MMMP_LAUNCH(cell_hist_kernel, grid_for(n, sms), 256, 0, stream, rows, ld, nd, n, bbox_d, bits, keys, hist);
+    int rc = mmmp_exclusive_scan_i32(hist, n_cells, offs, stream);
+    if (rc == MMMP_OK) {
+        MMMP_LAUNCH(cell_scatter_kernel, grid_for(n, sms), 256, 0, stream, keys, n, offs, hist + n_cells, perm);
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) rc = MMMP_ERR_CUDA_BASE + (int)e;
+    }
+    cudaFreeAsync(keys, s);
+    cudaFreeAsync(hist, s);
+    cudaFreeAsync(offs, s);
+    return rc;
+}
+
 }  // namespace
 
-extern "C" int mmmp_knn_stats(int enable, unsigned long long* out3_h) {
+extern "C" int mmmp_knn_stats(int enable, unsigned long long* out4_h) {
     if (enable && !g_knn_stats) {
-        MMMP_CUDA_TRY(cudaMalloc(&g_knn_stats, 3 * sizeof(unsigned long long)));
-        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, 3 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMalloc(&g_knn_stats, 4 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, 4 * sizeof(unsigned long long)));
     }
-    if (out3_h && g_knn_stats) {
+    if (out4_h && g_knn_stats) {
         MMMP_CUDA_TRY(cudaDeviceSynchronize());
-        MMMP_CUDA_TRY(cudaMemcpy(out3_h, g_knn_stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, 3 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMemcpy(out4_h, g_knn_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, 4 * sizeof(unsigned long long)));
     }
     if (!enable && g_knn_stats) {
         cudaFree(g_knn_stats);
@@ -438,13 +702,13 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     if (!W) return MMMP_ERR_LIMIT;
     const int F4 = W / 4;
     if (n_query == 0) return MMMP_OK;
+    mmmp_pool_keep();
     cudaStream_t s = (cudaStream_t)stream;
     int dev = 0, sms = 148, max_smem = 0;
     MMMP_CUDA_TRY(cudaGetDevice(&dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // queries per thread: as many as keep every SM busy with >= 2 CTAs of work
-    // (measured on B200: Q = 2 beats 4 and 8 for every row width -- more resident warps win)
+    // queries per thread (measured on B200: Q = 2 beats 4 and 8 -- more resident warps win)
     const int qmax = F4 <= 1 ? 8 : (F4 <= 2 ? 4 : (F4 <= 4 ? 2 : 1));
     int Q = 1;
     if (qmax >= 2 && n_query >= (int64_t)sms * KNN_CTHREADS * 2 * 2) Q = 2;
@@ -454,35 +718,77 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     }
     while (Q > 1 && scan_smem(F4, Q, k) > (size_t)max_smem) Q >>= 1;
     if (scan_smem(F4, Q, k) > (size_t)max_smem) return MMMP_ERR_LIMIT;
+    bool cull = !causal && n_ref >= KNN_CULL_MIN;
+    if (const char* e = getenv("MMMP_KNN_CULL")) cull = cull && atoi(e) != 0;
     const int n_qblocks = mmmp_div_up(n_query, (int64_t)KNN_CTHREADS * Q);
     const int64_t total_tiles = (n_ref + KNN_TILE - 1) / KNN_TILE;
     int n_splits = 1;
-    if (n_qblocks < 2 * sms) {
+    if (!cull && n_qblocks < 2 * sms) {
         n_splits = (2 * sms + n_qblocks - 1) / n_qblocks;
         if (n_splits > 32) n_splits = 32;
         if (n_splits > total_tiles) n_splits = (int)(total_tiles > 0 ? total_tiles : 1);
     }
-    // packed filter rows (library-owned, stream ordered)
-    float *pref = nullptr, *pquery = nullptr;
-    MMMP_CUDA_TRY(cudaMallocAsync(&pref, (size_t)(n_ref > 0 ? n_ref : 1) * W * sizeof(float), s));
-    if (n_ref > 0) {
-        int g = mmmp_div_up(n_ref, 256);
-        if (g > sms * 16) g = sms * 16;
-        MMMP_LAUNCH(knn_pack_kernel, g, 256, 0, stream, fref, ldf, fdim, n_ref, pref, W);
-    }
     const bool same = (fquery == fref && n_query == n_ref);
+    // temporaries (library-owned, stream ordered)
+    float *pref = nullptr, *pquery = nullptr, *boxes = nullptr;
+    int32_t *perm = nullptr, *qperm = nullptr, *tmp_idx = nullptr;
+    int* bbox = nullptr;
+    float* tmp_val = nullptr;
+    const int nd = fdim < 3 ? fdim : 3;
+    const size_t n_out = (size_t)n_query * n_splits * k;
+    auto cleanup = [&]() {
+        void* ptrs[] = {pref, same ? nullptr : pquery, boxes, perm, same ? nullptr : qperm, bbox, tmp_idx, tmp_val};
+        for (void* p : ptrs)
+            if (p) cudaFreeAsync(p, s);
+    };
+#define KNN_TRY(expr)                                       \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) {                            \
+            cleanup();                                      \
+            return MMMP_ERR_CUDA_BASE + (int)_e;            \
+        }                                                   \
+    } while (0)
+    KNN_TRY(cudaMallocAsync(&pref, (size_t)(n_ref > 0 ? n_ref : 1) * W * sizeof(float), s));
+    if (!same) KNN_TRY(cudaMallocAsync(&pquery, (size_t)n_query * W * sizeof(float), s));
+    KNN_TRY(cudaMallocAsync(&tmp_idx, n_out * sizeof(int32_t), s));
+    KNN_TRY(cudaMallocAsync(&tmp_val, n_out * sizeof(float), s));
+    if (cull) {
+        // grid resolution: ~16 rows per cell, 1..7 bits per axis
+        int bits = 1;
+        while (bits < 7 && ((int64_t)1 << (3 * (bits + 1))) * 16 <= n_ref) ++bits;
+        KNN_TRY(cudaMallocAsync(&bbox, 6 * sizeof(int), s));
+        const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+        KNN_TRY(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        MMMP_LAUNCH(bbox_kernel, grid_for(n_ref, sms), 256, 0, stream, fref, ldf, nd, n_ref, bbox);
+        KNN_TRY(cudaMallocAsync(&perm, sizeof(int32_t) * n_ref, s));
+        rc = spatial_perm(fref, ldf, nd, n_ref, bbox, bits, perm, stream, sms);
+        if (rc == MMMP_OK && !same) {
+            KNN_TRY(cudaMallocAsync(&qperm, sizeof(int32_t) * n_query, s));
+            rc = spatial_perm(fquery, ldf, nd, n_query, bbox, bits, qperm, stream, sms);
+        }
+        if (rc != MMMP_OK) {
+            cleanup();
+            return rc;
+        }
+        KNN_TRY(cudaMallocAsync(&boxes, sizeof(float) * 6 * (total_tiles > 0 ? total_tiles : 1), s));
+    }
+    if (n_ref > 0) MMMP_LAUNCH(knn_pack_kernel, grid_for(n_ref, sms), 256, 0, stream, fref, ldf, fdim, n_ref, perm, pref, W);
     if (same) {
         pquery = pref;
+        qperm = perm;
     } else {
-        MMMP_CUDA_TRY(cudaMallocAsync(&pquery, (size_t)n_query * W * sizeof(float), s));
-        int g = mmmp_div_up(n_query, 256);
-        if (g > sms * 16) g = sms * 16;
-        MMMP_LAUNCH(knn_pack_kernel, g, 256, 0, stream, fquery, ldf, fdim, n_query, pquery, W);
+        MMMP_LAUNCH(knn_pack_kernel, grid_for(n_query, sms), 256, 0, stream, fquery, ldf, fdim, n_query, qperm, pquery, W);
     }
+    if (cull && total_tiles > 0)
+        MMMP_LAUNCH(tile_box_kernel, (int)total_tiles, 256, 0, stream, pref, W, nd, n_ref, boxes);
     A.pref = pref;
     A.pquery = pquery;
     A.xref = xref;
     A.xquery = xquery;
+    A.perm = perm;
+    A.qperm = qperm;
+    A.boxes = boxes;
     A.n_ref = n_ref;
     A.n_query = n_query;
     A.query_id0 = query_id0;
@@ -493,11 +799,6 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     A.tiles_per_split = (int)((total_tiles + n_splits - 1) / n_splits);
     if (A.tiles_per_split < 1) A.tiles_per_split = 1;
     A.stats = g_knn_stats;
-    int32_t* tmp_idx = nullptr;
-    float* tmp_val = nullptr;
-    const size_t n_out = (size_t)n_query * n_splits * k;
-    MMMP_CUDA_TRY(cudaMallocAsync(&tmp_idx, n_out * sizeof(int32_t), s));
-    MMMP_CUDA_TRY(cudaMallocAsync(&tmp_val, n_out * sizeof(float), s));
     A.out_idx = tmp_idx;
     A.out_val = tmp_val;
     switch (F4 * 10 + Q) {
@@ -521,9 +822,7 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         cudaError_t e = cudaPeekAtLastError();
         if (e != cudaSuccess) rc = MMMP_ERR_CUDA_BASE + (int)e;
     }
-    cudaFreeAsync(tmp_idx, s);
-    cudaFreeAsync(tmp_val, s);
-    if (!same) cudaFreeAsync(pquery, s);
-    cudaFreeAsync(pref, s);
+    cleanup();
+#undef KNN_TRY
     return rc;
 }

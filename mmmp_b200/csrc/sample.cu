@@ -197,6 +197,7 @@ int grid_for(int64_t items, int block) {
 
 template <class In, int MODE>
 int scan_driver(const In* in, int64_t n, int64_t* out_offsets, int32_t* out_idx, int32_t* count, void* stream) {
+    mmmp_pool_keep();
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     int64_t* tmp = nullptr;

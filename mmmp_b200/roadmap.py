@@ -45,14 +45,40 @@ class PhaseTimer:
         return self.totals
 
 
+def shard_rows(n: int, rank: int, size: int):
+    """Contiguous row block [lo, hi) of rank `rank` out of `size` (last blocks may be short)."""
+    per = (n + size - 1) // size
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
+def all_gather_rows(t: torch.Tensor, size: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks in rank order; row counts may differ per rank.
+    Works on CUDA tensors over NCCL and on CPU tensors over gloo (tests)."""
+    if size == 1:
+        return t
+    import torch.distributed as dist
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    ns = [torch.empty_like(n) for _ in range(size)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(x.item()) for x in ns]
+    m = max(ns)
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(size)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([outs[g][: ns[g]] for g in range(size)], 0)
+
+
 class RoadmapBuilder:
     def __init__(self, world: core.SpatialWorld, robot: int = 0, metric: str = "fk", k: int = 10,
                  n_steps: int = 50, step: float = 0.02, flags: int = CHECK_SELF | CHECK_OBSTACLES,
-                 group=None, timer: Optional[PhaseTimer] = None, knn_pad: int = 6):
+                 group=None, timer: Optional[PhaseTimer] = None, knn_pad: int = 6, single_rank: bool = False):
         self.world, self.robot, self.metric, self.k = world, robot, metric, k
         self.n_steps, self.step, self.flags, self.knn_pad = n_steps, step, flags, knn_pad
         self.group = group
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if single_rank:
+            self.rank, self.size = 0, 1
+        elif group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.rank = torch.distributed.get_rank(group)
             self.size = torch.distributed.get_world_size(group)
         else:
@@ -69,22 +95,7 @@ class RoadmapBuilder:
 
     # ------------------------------------------------------------------ collectives
     def _all_gather_rows(self, t: torch.Tensor, counts=None) -> torch.Tensor:
-        """Concatenate per-rank row blocks in rank order (rows may differ per rank)."""
-        if self.size == 1:
-            return t
-        import torch.distributed as dist
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-        ns = torch.empty((self.size,), dtype=torch.int64, device=t.device)
-        dist.all_gather_into_tensor(ns, n, group=self.group)
-        ns = ns.tolist()
-        m = max(ns)
-        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[: t.shape[0]] = t
-        out = torch.empty((self.size * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, pad, group=self.group)
-        if all(x == m for x in ns):
-            return out
-        return torch.cat([out[g * m: g * m + ns[g]] for g in range(self.size)], 0)
+        return all_gather_rows(t, self.size, self.group)
 
     # ------------------------------------------------------------------ sampling
     def sample_free(self, n: int, seed: int, oversample: float = 1.05, first_index: int = 0):
@@ -98,9 +109,12 @@ class RoadmapBuilder:
             m = ((m + self.size - 1) // self.size) * self.size
             per = m // self.size
             q64, q32 = core.sample_uniform(self.lo, self.hi, per, seed, first + self.rank * per)
+            self._mark("sample")
             hit = self.world.collide_configs(q32, self.robot, self.flags)
+            self._mark("config_collision")
             idx = core.compact_free(hit)
             f64 = core.gather_rows(q64, idx)
+            self._mark("compact")
             f64 = self._all_gather_rows(f64)
             rate = max(f64.shape[0] / m, 1e-3)
             got64.append(f64)
@@ -109,7 +123,7 @@ class RoadmapBuilder:
         self.accept_rate = rate
         q64 = (got64[0] if len(got64) == 1 else torch.cat(got64, 0))[:n].contiguous()
         q32 = core.pack_f32(q64)
-        self._mark("sample+config_collision")
+        self._mark("gather_samples")
         return q64, q32
 
     # ------------------------------------------------------------------ neighbour search + edges
@@ -122,8 +136,7 @@ class RoadmapBuilder:
         """k nearest candidates of every node + the verdict of every candidate edge.
         -> dict(idx [n,k] int32, dist [n,k] fp64, edge_free [n,k] uint8, ambiguous [n] uint8)"""
         n = q64.shape[0]
-        per = (n + self.size - 1) // self.size
-        lo, hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
+        lo, hi = shard_rows(n, self.rank, self.size)
         feats = self.features(q64, q32)
         mine = feats.rows(lo, hi)
         self._mark("features")

@@ -89,6 +89,10 @@ def table_hit(model, q):
 def self_hit(model, w, r, l, q=None, use_tables=True):
     pairs = {(a, b) for a, b in model["self_pairs"]}
     hit = np.zeros(w.shape[0], bool)
+    if use_tables:
+        for a, b in model.get("proven_free_pairs", []):      # proven never to collide: not tested
+            pairs.discard((a, b))
+            pairs.discard((b, a))
     if use_tables and q is not None:
         hit |= table_hit(model, q)
         for pt in model.get("pair_tables", []):

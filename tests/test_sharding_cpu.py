@@ -1,0 +1,63 @@
+"""CPU suite, world_size 2 over gloo: the host-side logic of the multi-GPU path
+(mmmp_b200/roadmap.py) -- contiguous row sharding, rank-ordered gather of ragged row blocks,
+and the counter-based sampling blocks that make the sharded node order identical to the
+single-GPU order (checked with the oracle restatement of the Philox sampler)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from mmmp_b200.roadmap import all_gather_rows, shard_rows
+        from oracle import sampling
+        ok = True
+        # ragged gather: rank r contributes r + 2 rows
+        t = torch.full((rank + 2, 3), float(rank)) + torch.arange(rank + 2)[:, None]
+        g = all_gather_rows(t, size)
+        want = torch.cat([torch.full((r + 2, 3), float(r)) + torch.arange(r + 2)[:, None] for r in range(size)])
+        ok &= bool((g == want).all())
+        # equal blocks and an empty block
+        e = all_gather_rows(torch.zeros((0, 2)) if rank == 1 else torch.ones((4, 2)), size)
+        ok &= e.shape == (4, 2)
+        # row sharding covers [0, n) exactly once, in rank order
+        for n in (1, 7, 1000, 1001):
+            lo, hi = shard_rows(n, rank, size)
+            blocks = all_gather_rows(torch.arange(lo, hi)[:, None], size)
+            ok &= bool((blocks[:, 0] == torch.arange(n)).all())
+        # sampling blocks: rank r draws candidates [first + r*per, first + (r+1)*per); the rank-ordered
+        # concatenation equals the single-rank stream (counter-based generator)
+        lo_, hi_ = np.array([-2.0, 0.0, -1.0]), np.array([2.0, 3.0, 1.0])
+        per, first, seed = 500, 12345, 99
+        mine = sampling.sample_uniform(lo_, hi_, per, seed, first + rank * per)
+        free = mine[mine[:, 0] > -1.0]                       # a stand-in for the collision filter
+        allf = all_gather_rows(torch.from_numpy(free), size).numpy()
+        single = sampling.sample_uniform(lo_, hi_, per * size, seed, first)
+        ok &= bool((allf == single[single[:, 0] > -1.0]).all())
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_logic_world_size_2():
+    size = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(size, _free_port(), out), nprocs=size, join=True)
+    assert all(out.get(r) for r in range(size)), dict(out)
