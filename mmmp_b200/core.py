@@ -511,14 +511,21 @@ class SpatialWorld(_World):
         return out
 
     def roadmap_candidates_host(self, q64: np.ndarray, robot: int, metric_kind: int, k: int, n_steps: int,
-                                step: float, flags: int = CHECK_SELF | CHECK_OBSTACLES):
-        """Host arrays in, host arrays out (the e2e call): see include/mmmp_b200.h."""
+                                step: float, flags: int = CHECK_SELF | CHECK_OBSTACLES, pinned: bool = False):
+        """Host arrays in, host arrays out (the e2e call): see include/mmmp_b200.h.
+        pinned=True returns the outputs in page-locked host memory (views of torch tensors)."""
         q64 = np.ascontiguousarray(q64, dtype=np.float64)
         N, D = q64.shape
-        node_src = np.empty((N,), dtype=np.int32)
-        nbr = np.empty((N, k), dtype=np.int32)
-        dist = np.empty((N, k), dtype=np.float64)
-        free = np.empty((N, k), dtype=np.uint8)
+
+        def host(shape, np_dtype, t_dtype):
+            if pinned:
+                return torch.empty(shape, dtype=t_dtype, pin_memory=True).numpy()
+            return np.empty(shape, dtype=np_dtype)
+
+        node_src = host((N,), np.int32, torch.int32)
+        nbr = host((N, k), np.int32, torch.int32)
+        dist = host((N, k), np.float64, torch.float64)
+        free = host((N, k), np.uint8, torch.uint8)
         n_nodes = C.c_int64(0)
         timings = np.zeros((8,), dtype=np.float32)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731

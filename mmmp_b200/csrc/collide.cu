@@ -177,8 +177,7 @@ __device__ bool spatial_in_collision(const WorldDev* __restrict__ Wg, const Spat
             for (int i = 0; i < 12; ++i) p[i * stride] = T.m[i];
             if (n_obs > 0) {
                 // links hanging off frame j+1: bounding sphere first, spheres on demand
-                for (int l = 0; l < R.n_links; ++l) {
-                    if (R.link_frame[l] != j + 1) continue;
+                for (int l = R.frame_link_begin[j + 1]; l < R.frame_link_begin[j + 2]; ++l) {
                     const float4 B = R.link_bound[l];
                     if (B.w < 0.f) continue;
                     const float3 wb = affine_point(T, B.x, B.y, B.z);
@@ -276,12 +275,17 @@ collide_pairs_kernel(SpatialArgs A, const float* __restrict__ qa, const float* _
     }
 }
 
-// one warp per edge; lane l takes steps l*rounds + r in round r so that every
-// round spreads over the whole edge (early exit after the first ballot that
-// sees a hit).  Verdict = OR over all steps = reference semantics.
+// Edge checks.  A warp is split into groups of L lanes; one group = one edge, lane g of the
+// group takes steps g*rounds + r in round r (every round spreads over the whole edge).  After
+// each round a warp ballot tells every group whether one of its steps collided: that edge is
+// decided (early exit) and its lanes idle until all groups of the warp are done.  L is chosen
+// on the host so that rounds * L wastes the fewest lanes (50 steps: L = 10 -> 3 edges per
+// warp, 5 rounds, 94 % lane use; consecutive edges of a k-NN table share their first node,
+// so the groups of a warp see similar configurations).  Verdict = OR over all steps =
+// reference semantics (decoupled_prm.py:855-863).
 __global__ void __launch_bounds__(128)
 collide_edges_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base, int ld,
-                     const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
+                     const int32_t* __restrict__ edges, int64_t E, int n_steps, double step, int L,
                      uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     SpatialSmem* hdr;
@@ -293,33 +297,46 @@ collide_edges_kernel(SpatialArgs A, const float* __restrict__ qa_base, const flo
     const int stride = blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
-    const int rounds = (n_steps + 31) >> 5;
-    for (int64_t e = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); e < E;
-         e += (int64_t)gridDim.x * warps_per_cta) {
-        const float *pa, *pb;
-        if (edges) {
-            const int ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
-            if (ia < 0 || ib < 0) {  // empty neighbour slot: reported as blocked
-                if (lane == 0) out[e] = 1;
-                continue;
+    const int epw = 32 / L;                 // edges per warp
+    const int group = lane / L, gl = lane - group * L;
+    const bool in_group = group < epw;
+    const int rounds = (n_steps + L - 1) / L;
+    const unsigned gmask = in_group ? (((L == 32) ? 0xffffffffu : ((1u << L) - 1u)) << (group * L)) : 0u;
+    const int64_t warp_id = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
+    for (int64_t e0 = warp_id * epw; e0 < E; e0 += n_warps * epw) {
+        const int64_t e = e0 + group;
+        bool valid = in_group && e < E;
+        const float *pa = qa_base, *pb = qa_base;
+        bool blocked = false;   // empty neighbour slot: reported as blocked
+        if (valid) {
+            if (edges) {
+                const int ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
+                blocked = ia < 0 || ib < 0;
+                pa = qa_base + (int64_t)(blocked ? 0 : ia) * ld;
+                pb = qa_base + (int64_t)(blocked ? 0 : ib) * ld;
+            } else {
+                pa = qa_base + e * ld;
+                pb = qb_base + e * ld;
             }
-            pa = qa_base + (int64_t)ia * ld;
-            pb = qa_base + (int64_t)ib * ld;
-        } else {
-            pa = qa_base + e * ld;
-            pb = qb_base + e * ld;
         }
-        bool any = false;
-        for (int r = 0; r < rounds && !any; ++r) {
-            const int i = lane * rounds + r;
+        bool done = blocked || !valid;
+        bool collided = blocked;
+        for (int r = 0; r < rounds; ++r) {
+            const int i = gl * rounds + r;
             bool hit = false;
-            if (i < n_steps) {
+            if (!done && i < n_steps) {
                 QEdge ql{pa, pb, (float)((double)i * step)};
                 hit = spatial_in_collision(A.W, hdr, robs, obs, A.flags, cs, stride, ql);
             }
-            any = __any_sync(0xffffffffu, hit);
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            if (ballot & gmask) {
+                collided = true;
+                done = true;
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
-        if (lane == 0) out[e] = any ? 1 : 0;
+        if (valid && gl == 0) out[e] = collided ? 1 : 0;
     }
 }
 
@@ -444,9 +461,23 @@ static int launch_edges(const mmmp_world* w, int robot, const float* qa, const f
     size_t smem;
     rc = pick_launch(collide_edges_kernel, w, A, 4, E, block, smem, grid);
     if (rc) return rc;
-    const int wpc = block / 32;
+    // lanes per edge: minimise rounds / (edges per warp)
+    int L = 32;
+    {
+        const int cand[6] = {32, 16, 10, 8, 5, 4};
+        double best = 1e30;
+        for (int c = 0; c < 6; ++c) {
+            const int l = cand[c];
+            const double cost = (double)((n_steps + l - 1) / l) / (double)(32 / l);
+            if (cost < best - 1e-12) {
+                best = cost;
+                L = l;
+            }
+        }
+    }
+    const int wpc = block / 32 * (32 / L);  // edges per CTA pass
     grid = mmmp_div_up(E, wpc) < grid ? mmmp_div_up(E, wpc) : grid;
-    MMMP_LAUNCH(collide_edges_kernel, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps, step, out);
+    MMMP_LAUNCH(collide_edges_kernel, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps, step, L, out);
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }

@@ -45,7 +45,8 @@ struct RobotDev {
     float base[12];
     float origin[MMMP_MAX_JOINTS + 1][12];
     float4 link_bound[MMMP_MAX_LINKS];  // bounding sphere, frame local (frame-0 links: WORLD)
-    int link_frame[MMMP_MAX_LINKS];
+    int link_frame[MMMP_MAX_LINKS];              // non-decreasing in the link id
+    int frame_link_begin[MMMP_MAX_JOINTS + 2];   // links of frame f: [begin[f], begin[f+1])
     int link_sphere_begin[MMMP_MAX_LINKS + 1];
     uchar2 self_pair[MMMP_MAX_SELF_PAIRS];
     PairTableDev table[MMMP_MAX_PAIR_TABLES];

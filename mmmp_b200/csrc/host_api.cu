@@ -27,11 +27,17 @@ invert_flags_kernel(uint8_t* f, int64_t n) {
         f[i] = f[i] ? 0 : 1;
 }
 
-struct DevBuf {
+thread_local cudaStream_t tl_alloc_stream = nullptr;  // stream the host call allocates on
+
+struct DevBuf {  // stream-ordered temporaries from the (cached) default pool
     void* p = nullptr;
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t bytes) {
+        s = tl_alloc_stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 16, s);
+    }
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, s);
     }
     template <class T>
     T* as() { return reinterpret_cast<T*>(p); }
@@ -99,8 +105,10 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
     int kc = k + 6;
     if (kc > MMMP_MAX_K) kc = MMMP_MAX_K;
 
+    mmmp_pool_keep();
     cudaStream_t s;
     MMMP_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    tl_alloc_stream = s;
     cudaEvent_t ev[9];
     for (auto& e : ev) cudaEventCreate(&e);
     int rc = MMMP_OK;

@@ -135,6 +135,14 @@ extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
                                           (float)d.sphere[s][2], (float)d.sphere[s][3]);
             }
         }
+        for (int f = 0; f < MMMP_MAX_JOINTS + 2; ++f) R.frame_link_begin[f] = 0;
+        for (int l = 0; l < d.n_links; ++l) {
+            if (l > 0 && d.link_frame[l] < d.link_frame[l - 1]) {  // links must be ordered by frame
+                free(H);
+                return MMMP_ERR_ARG;
+            }
+            for (int f = d.link_frame[l] + 1; f < MMMP_MAX_JOINTS + 2; ++f) R.frame_link_begin[f]++;
+        }
         R.n_moving_links = 0;
         for (int l = 0; l < d.n_links; ++l) {
             bounding_sphere(R.sphere + R.link_sphere_begin[l], R.link_sphere_begin[l + 1] - R.link_sphere_begin[l],

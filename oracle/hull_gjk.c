@@ -164,7 +164,10 @@ static int closest_tetra(double p[][3], double* out) {
         sub3(d, a, ad);
         const double sd = dot3(n, ad);        /* side of the opposite vertex */
         const double so = -dot3(n, a);        /* side of the origin */
-        if (sd == 0.0) { /* degenerate (flat) tetra: treat face as candidate */
+        /* flat tetra (the fourth vertex within rounding of the face plane): the side tests
+         * below would be decided by noise and could report a bogus containment, so the
+         * face is only a candidate for the closest feature */
+        if (fabs(sd) <= 1e-10 * sqrt(dot3(n, n) * dot3(ad, ad))) {
             outside_any = 1;
         } else if ((so > 0) == (sd > 0) || so == 0.0) {
             continue; /* origin on the inner side of this face */

@@ -139,3 +139,14 @@ def test_hull_oracle_known_answers():
         w = rng.dirichlet(np.ones(4), size=(2, 4000))
         ub = np.linalg.norm((w[0] @ a)[:, None] - (w[1] @ b)[None], axis=-1).min()
         assert d <= ub + 1e-9 and d > ub - 0.25
+    # a pose where GJK builds a flat tetrahedron (regression: sign noise read as containment):
+    # the distance must not depend on the frame the pair is posed in
+    from mmmp_b200 import core
+    q = np.array([[0.31, 0.35, -0.84, -1.26, 1.33, 0.33, 0.21]])
+    P = hull.link_poses(q, core.base_matrix((0, 0, 0.01)))
+    H = hull.hulls()
+    TA, TB = P[:, hull.LINK_FRAME[5]], P[:, hull.LINK_FRAME[7]]
+    d_world = hull.posed_distance(H[5], TA, H[7], TB)[0]
+    d_local = hull.posed_distance(H[5], np.eye(4)[None], H[7], (np.linalg.inv(TA[0]) @ TB[0])[None])[0]
+    assert d_world == pytest.approx(d_local, abs=1e-9) and d_world == pytest.approx(0.01106909, abs=1e-7)
+    assert not hull.PandaHullChecker([core.base_matrix((0, 0, 0.01))]).self_collision(q)[0]

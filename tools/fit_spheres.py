@@ -121,7 +121,12 @@ def fit_link(verts, eps, floor_z=None, floor_eps=None, cand_spacing=0.006, samp_
     margin = float((radii - depth).max())
     chk, _, _ = sample_hull(verts, samp_spacing * 0.7)
     unc_d = (np.sqrt(((chk[:, None, :] - centres[None]) ** 2).sum(-1)) - radii[None]).min(1)
-    return centres, radii, margin, float(unc_d.max()), int(unc.sum())
+    # coverage pad: the cover was built on a point sample; inflate by the worst gap the finer
+    # check sample shows (+0.3 mm) so that the union of spheres contains the hull for certain
+    cov_pad = max(float(unc_d.max()), 0.0) + 0.0003
+    radii = radii + cov_pad
+    margin += cov_pad
+    return centres, radii, margin, float(unc_d.max()) - cov_pad, int(unc.sum())
 
 
 def rpy_matrix(rpy):
