@@ -128,7 +128,10 @@ enum {
     MMMP_CHECK_SELF = 1,        /* env.py:77-84 / planar env.py:208-217              */
     MMMP_CHECK_OBSTACLES = 2,   /* env.py:51-68 / planar env.py:148-205              */
     MMMP_CHECK_ROBOTS = 4,      /* env.py:70-75 / planar env.py:78-117               */
-    MMMP_CHECK_BOUNDS = 8       /* planar env.py:220-229 (ignored by spatial worlds) */
+    MMMP_CHECK_BOUNDS = 8,      /* planar env.py:220-229 (ignored by spatial worlds) */
+    MMMP_CHECK_EXHAUSTIVE = 16  /* edge checks only: evaluate every interpolation step even
+                                   when a clearance bound already proves it free (same
+                                   verdicts; the cross-check of the default path)       */
 };
 
 /* ---- (a) joint-space sampling -------------------------------------------
@@ -195,8 +198,11 @@ int mmmp_collide_configs(const mmmp_world* w, int robot, const void* q_d, int ld
 /* is_collision_free_edge (decoupled_prm.py:855-863, coupled_prm.py:179-187,
  * planar single_arm/prm.py:161-169): for t = i*step, i in [0, n_steps):
  * q = qa + t (qb - qa); out_d[e] = 1 if ANY interpolant collides.
- * edges_d [E,2] int32 rows (a, b) index q_d; one warp per edge, lanes are
- * interpolation steps, warp-ballot early exit.                             */
+ * edges_d [E,2] int32 rows (a, b) index q_d.  Spatial worlds with
+ * n_steps <= 64 evaluate a step only when no earlier evaluation of the same
+ * edge proves it free: an evaluation returns the clearance of the sphere
+ * model, and |d centre / d q_m| <= lever arm bounds how far every sphere can
+ * move per step, so the verdict equals the OR over all steps.               */
 int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
                        const int32_t* edges_d, int64_t E, int n_steps, double step,
                        uint32_t flags, uint8_t* out_d, void* stream);
@@ -205,6 +211,10 @@ int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
 int mmmp_collide_segments(const mmmp_world* w, int robot, const void* qa_d, const void* qb_d,
                           int ld, int64_t E, int n_steps, double step,
                           uint32_t flags, uint8_t* out_d, void* stream);
+/* profiling aid: enable != 0 turns on two device counters of the spatial edge
+ * kernels (edges decided, configurations evaluated); out2_h (may be NULL)
+ * receives and resets them; enable == 0 frees them.                         */
+int mmmp_edge_stats(int enable, unsigned long long* out2_h);
 /* robot_robot_collision(q1, q2, r1, r2) on a pair list
  * (decoupled_prm.py:871-876; cbsprm.py:165-183): qa_d rows are robot ra's
  * joints, qb_d rows robot rb's.                                            */

@@ -21,7 +21,7 @@ MAX_GROUPS = 8
 
 OBS_PLANE, OBS_SPHERE, OBS_BOX, OBS_CYLINDER = 0, 1, 2, 3
 POBS_RECT, POBS_CIRCLE = 0, 1
-CHECK_SELF, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_BOUNDS = 1, 2, 4, 8
+CHECK_SELF, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_BOUNDS, CHECK_EXHAUSTIVE = 1, 2, 4, 8, 16
 METRIC_L2, METRIC_GROUP_L2_SUM, METRIC_SQ_SUM = 0, 1, 2
 
 
@@ -113,6 +113,7 @@ SIGNATURES = {
     "mmmp_gather_rows": [_P, _I, _P, _I64, _P, _P],
     "mmmp_knn": [_P, _P, _I64, _P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _I, _I64, _P, _P, _P],
     "mmmp_knn_stats": [_I, _P],
+    "mmmp_edge_stats": [_I, _P],
     "mmmp_knn_refine": [_P, _P, _I, C.POINTER(Metric), _P, _P, _I64, _I, _I, _D, _P, _P, _P, _P],
     "mmmp_radius": [_P, _P, _I64, _P, _P, _I64, _I, _I, C.POINTER(Metric), C.POINTER(Metric), _D, _I, _I, _I, _I,
                     _I64, _P, _P, _P, _P, _P],

@@ -1,30 +1,44 @@
 // Kernel (c): configuration and discretised-edge collision checks for spatial
 // (Panda / KUKA) worlds.  One configuration per thread: FK of the serial chain
 // with link transforms staged in shared memory; the thread parks its 3x4 frame
-// poses in a private shared-memory column (conflict-free, lane-contiguous).
+// poses and the world-space centres of its link bounding spheres in a private
+// shared-memory column (conflict-free, lane-contiguous).
 // Every collision link carries a sphere decomposition fitted offline plus a
 // bounding sphere: obstacle, self and robot-robot tests first cull on the
 // bounding spheres and only then descend to the sphere level, where one link's
 // spheres are mapped into the OTHER link's frame so the inner loop reads its
 // constants as shared-memory broadcasts.  Link pairs whose relative pose depends
 // on two joints only may be decided by an exact offline bit table instead.
-// Edge checks map one warp to one edge (lanes = interpolation steps) with
-// warp-ballot early exit.
+//
+// Edge checks (OR over the interpolation steps) do not evaluate every step: an
+// evaluation also yields the clearance of the sphere model at that step, and the
+// lever arms RobotDev::reach bound how far any sphere centre can travel per unit
+// of the interpolation parameter, so one evaluation proves a whole interval of
+// steps collision free.  The verdict is the same OR over all steps (the skipped
+// ones are proven free with a 0.1 mm slack that absorbs fp32 rounding); the
+// exhaustive kernel is kept as the cross-check (MMMP_CHECK_EXHAUSTIVE).
 //
 // Replaces (reference): Environment.robot_self_collision / robot_obstacle_collision /
 // robot_robot_collision planners/prm/pybullet/env.py:51-84 as composed by
 // DecoupledPRM.is_collision_free_sample / _edge decoupled_prm.py:840-863 and
 // CoupledPRM.is_collision_free_sample / _edge coupled/coupled_prm.py:143-187.
+#include <cstdlib>
 #include "common.cuh"
 #include "obstacle.cuh"
 
 namespace {
 
+#define MMMP_GAP_SLACK 1.0e-4f   // metres: clearance kept in hand when a step is skipped
+
 struct SpatialSmem {
     int n_r;
     int n_obs;
+    int slots;                         // frame slots per thread (sum of n_joints)
+    int links;                         // link slots per thread (sum of n_links)
+    int any_tables;
     int col[MMMP_MAX_ROBOTS];          // first column of local robot lr in a q row
     int frame_slot[MMMP_MAX_ROBOTS];   // first frame slot of local robot lr
+    int link_slot[MMMP_MAX_ROBOTS];    // first link slot of local robot lr
 };
 
 struct SpatialArgs {
@@ -33,13 +47,21 @@ struct SpatialArgs {
     int robots[MMMP_MAX_ROBOTS];
     int col[MMMP_MAX_ROBOTS];
     uint32_t flags;
-    int slots;  // frame slots (12 floats each) per thread
+    int slots;  // frame slots per thread
+    int links;  // link slots per thread
 };
+
+// per-thread shared-memory column, element e of this thread at fr[e * stride]:
+//   [0, 12*slots)                 frame poses (row-major 3x4), slot = frame - 1
+//   [12*slots, +3*links)          world centres of the link bounding spheres
+//   [12*slots + 3*links, +slots)  travel bound of each frame per unit t (edge checks)
+#define MMMP_COLUMN_FLOATS(slots, links) (13 * (slots) + 3 * (links))
 
 // --- q loaders -------------------------------------------------------------
 struct QConfig {
     const float* row;
     __device__ __forceinline__ float get(int lr, int c) const { return __ldg(row + c); }
+    __device__ __forceinline__ float delta(int lr, int c) const { return 0.f; }
 };
 struct QEdge {
     const float* a;
@@ -49,11 +71,13 @@ struct QEdge {
         const float qa = __ldg(a + c), qb = __ldg(b + c);
         return fmaf(t, qb - qa, qa);
     }
+    __device__ __forceinline__ float delta(int lr, int c) const { return __ldg(b + c) - __ldg(a + c); }
 };
 struct QPair {
     const float* ra;
     const float* rb;
     __device__ __forceinline__ float get(int lr, int c) const { return __ldg((lr == 0 ? ra : rb) + c); }
+    __device__ __forceinline__ float delta(int lr, int c) const { return 0.f; }
 };
 
 __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -72,12 +96,19 @@ __device__ __forceinline__ void stage_world(const SpatialArgs& A, unsigned char*
     if (threadIdx.x == 0) {
         hdr->n_r = A.n_r;
         hdr->n_obs = n_obs;
-        int slot = 0;
+        hdr->slots = A.slots;
+        hdr->links = A.links;
+        int slot = 0, lslot = 0, tables = 0;
         for (int lr = 0; lr < A.n_r; ++lr) {
+            const RobotDev& R = A.W->robots[A.robots[lr]];
             hdr->col[lr] = A.col[lr];
             hdr->frame_slot[lr] = slot;
-            slot += A.W->robots[A.robots[lr]].n_joints;
+            hdr->link_slot[lr] = lslot;
+            slot += R.n_joints;
+            lslot += R.n_links;
+            tables += R.n_tables;
         }
+        hdr->any_tables = tables;
     }
     for (int lr = 0; lr < A.n_r; ++lr) {
         const int* src = reinterpret_cast<const int*>(&A.W->robots[A.robots[lr]]);
@@ -105,17 +136,17 @@ __device__ __forceinline__ void load_frame(Affine& T, const float* fr, int strid
     for (int i = 0; i < 12; ++i) T.m[i] = p[i * stride];
 }
 
-// spheres of link lb (robot RB, pose TB) against spheres of link la (robot RA, pose TA)
+__device__ __forceinline__ float fast_sqrt(float x) { return x * rsqrtf(fmaxf(x, 1e-30f)); }
+
+// spheres of link lb (robot RB, pose TB) against spheres of link la (robot RA, pose TA); the
+// caller has already found the two bounding spheres overlapping (GAP: closer than `want`).
+// With GAP the smallest clearance met on the way is folded into `gap`: a lower bound of the
+// true one, exact wherever it is below `want` (a sphere of B further than `want` from A's
+// bounding sphere contributes that distance instead of its exact clearance).
+template <bool GAP>
 __device__ __forceinline__ bool link_pair_hit(const RobotDev& RA, int la, const Affine& TA, const RobotDev& RB, int lb,
-                                              const Affine& TB) {
-    const float4 ba = RA.link_bound[la], bb = RB.link_bound[lb];
-    const float3 wa = affine_point(TA, ba.x, ba.y, ba.z);
-    const float3 wb = affine_point(TB, bb.x, bb.y, bb.z);
-    {
-        const float dx = wa.x - wb.x, dy = wa.y - wb.y, dz = wa.z - wb.z;
-        const float rr = ba.w + bb.w;
-        if (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) > rr * rr) return false;
-    }
+                                              const Affine& TB, float want, float& gap) {
+    const float4 ba = RA.link_bound[la];
     // M = TA^-1 * TB  (rigid): R = RA^T RB, t = RA^T (tB - tA)
     Affine M;
 #pragma unroll
@@ -134,115 +165,220 @@ __device__ __forceinline__ bool link_pair_hit(const RobotDev& RA, int la, const 
         {
             const float dx = c.x - ba.x, dy = c.y - ba.y, dz = c.z - ba.z;
             const float rr = S.w + ba.w;
-            if (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) > rr * rr) continue;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            if (GAP) {  // clearance already as large as the caller can use: no need for the exact one
+                const float gs = fast_sqrt(d2) - rr;
+                if (gs > want) {
+                    gap = fminf(gap, gs);
+                    continue;
+                }
+            } else if (d2 > rr * rr) {
+                continue;
+            }
         }
+        float m2 = 3.0e38f;
         for (int sa = a0; sa < a1; ++sa) {
             const float4 P = RA.sphere[sa];
             const float dx = c.x - P.x, dy = c.y - P.y, dz = c.z - P.z;
             const float rr = S.w + P.w;
-            hit |= fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            hit |= d2 <= rr * rr;
+            if (GAP) m2 = fminf(m2, fast_sqrt(d2) - rr);
         }
         if (hit) return true;
+        if (GAP) gap = fminf(gap, m2);
     }
     return false;
 }
 
 template <class QL>
-__device__ bool spatial_in_collision(const WorldDev* __restrict__ Wg, const SpatialSmem* hdr, const RobotDev* robs,
-                                     const ObstacleDev* obs, uint32_t flags, float* fr, int stride, const QL& ql) {
+__device__ __forceinline__ bool tables_hit(const WorldDev* __restrict__ Wg, const RobotDev& R, int lr, int col,
+                                           const QL& ql) {
+    for (int t = 0; t < R.n_tables; ++t) {
+        const PairTableDev& P = R.table[t];
+        const float qu = ql.get(lr, col + P.joint_u), qw = ql.get(lr, col + P.joint_v);
+        int iu = (int)floorf((qu - P.lo_u) * P.inv_du);
+        int iv = (int)floorf((qw - P.lo_v) * P.inv_dv);
+        iu = min(max(iu, 0), P.n_u - 1);
+        iv = min(max(iv, 0), P.n_v - 1);
+        const int cell = iu * P.n_v + iv;
+        if ((__ldg(Wg->table_bits + P.word_offset + (cell >> 5)) >> (cell & 31)) & 1u) return true;
+    }
+    return false;
+}
+
+// One configuration.  Returns < 0 when it is in collision.  Otherwise: GAP = false returns 1;
+// GAP = true returns the half-width, in units of the interpolation parameter t, of the
+// interval around this configuration's t on which the edge ql is proven collision free
+// (0 when nothing can be proven).  The collision verdict is computed by the same
+// expressions for both values of GAP.  skip_tables: the caller has looked up the pair
+// tables itself.  t_want (GAP): the half-width the caller would like; a bounding-sphere
+// clearance that already proves it is taken as is, a smaller one is refined at the sphere
+// level (tighter, dearer).
+template <class QL, bool GAP>
+__device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem* hdr, const RobotDev* robs,
+                              const ObstacleDev* obs, uint32_t flags, float* fr, int stride, const QL& ql,
+                              bool skip_tables, float t_want) {
+    const float HIT = -1.f;
+    const float INF = __int_as_float(0x7f800000);
     const int n_r = hdr->n_r;
     const int n_obs = (flags & MMMP_CHECK_OBSTACLES) ? hdr->n_obs : 0;
+    float* cen = fr + (size_t)hdr->slots * 12 * stride;
+    float* vel = cen + (size_t)hdr->links * 3 * stride;
+    float tsafe = INF;
     for (int lr = 0; lr < n_r; ++lr) {
         const RobotDev& R = robs[lr];
         const int col = hdr->col[lr];
-        if (n_obs > 0 && R.base_hits_obstacles) return true;
+        if (n_obs > 0 && R.base_hits_obstacles) return HIT;
         Affine T;
         affine_load(T, R.base);
         const int slot0 = hdr->frame_slot[lr];
+        float* cl = cen + (size_t)hdr->link_slot[lr] * 3 * stride;
+        for (int l = R.frame_link_begin[0]; l < R.frame_link_begin[1]; ++l) {  // base links: world coordinates
+            const float4 B = R.link_bound[l];
+            cl[(3 * l + 0) * stride] = B.x;
+            cl[(3 * l + 1) * stride] = B.y;
+            cl[(3 * l + 2) * stride] = B.z;
+        }
         bool hit = false;
-        float qv[MMMP_MAX_JOINTS];
+        float adq[MMMP_MAX_JOINTS];
 #pragma unroll
-        for (int j = 0; j < MMMP_MAX_JOINTS; ++j) qv[j] = 0.f;
+        for (int j = 0; j < MMMP_MAX_JOINTS; ++j) adq[j] = 0.f;
 #pragma unroll 1
         for (int j = 0; j < R.n_joints; ++j) {
             const float qj = ql.get(lr, col + j);
-#pragma unroll
-            for (int jj = 0; jj < MMMP_MAX_JOINTS; ++jj)
-                if (jj == j) qv[jj] = qj;
             float s, c;
             sincosf(qj, &s, &c);
             affine_step(T, R.origin[j], s, c);
             float* p = fr + (size_t)(slot0 + j) * 12 * stride;
 #pragma unroll
             for (int i = 0; i < 12; ++i) p[i * stride] = T.m[i];
-            if (n_obs > 0) {
-                // links hanging off frame j+1: bounding sphere first, spheres on demand
-                for (int l = R.frame_link_begin[j + 1]; l < R.frame_link_begin[j + 2]; ++l) {
-                    const float4 B = R.link_bound[l];
-                    if (B.w < 0.f) continue;
-                    const float3 wb = affine_point(T, B.x, B.y, B.z);
-                    for (int o = 0; o < n_obs; ++o) {
-                        if (!sphere_hits_obstacle(wb.x, wb.y, wb.z, B.w, obs[o])) continue;
-                        for (int sp = R.link_sphere_begin[l]; sp < R.link_sphere_begin[l + 1]; ++sp) {
-                            const float4 S = R.sphere[sp];
-                            const float3 w = affine_point(T, S.x, S.y, S.z);
-                            hit |= sphere_hits_obstacle(w.x, w.y, w.z, S.w, obs[o]);
-                        }
-                        if (hit) return true;
+            float inv_v = 0.f, want = 0.f;
+            if (GAP) {
+                const float dj = fabsf(ql.delta(lr, col + j));
+                float v = 0.f;
+#pragma unroll
+                for (int m = 0; m < MMMP_MAX_JOINTS; ++m) {
+                    if (m == j) adq[m] = dj;
+                    if (m <= j) v = fmaf(adq[m], R.reach[m][j + 1], v);
+                }
+                vel[(slot0 + j) * stride] = v;
+                inv_v = __fdividef(1.f, fmaxf(v, 1e-20f));
+                want = fmaf(v, t_want, MMMP_GAP_SLACK);
+            }
+            float gmin = INF;
+            // links hanging off frame j+1: bounding sphere first, spheres on demand
+            for (int l = R.frame_link_begin[j + 1]; l < R.frame_link_begin[j + 2]; ++l) {
+                const float4 B = R.link_bound[l];
+                if (B.w < 0.f) continue;
+                const float3 wb = affine_point(T, B.x, B.y, B.z);
+                cl[(3 * l + 0) * stride] = wb.x;
+                cl[(3 * l + 1) * stride] = wb.y;
+                cl[(3 * l + 2) * stride] = wb.z;
+                for (int o = 0; o < n_obs; ++o) {
+                    float g = INF;
+                    const bool bound_hit = sphere_vs_obstacle<GAP>(wb.x, wb.y, wb.z, B.w, obs[o], g);
+                    if (GAP ? g > want : !bound_hit) {
+                        if (GAP) gmin = fminf(gmin, g);
+                        continue;
                     }
+                    for (int sp = R.link_sphere_begin[l]; sp < R.link_sphere_begin[l + 1]; ++sp) {
+                        const float4 S = R.sphere[sp];
+                        const float3 w = affine_point(T, S.x, S.y, S.z);
+                        hit |= sphere_vs_obstacle<GAP>(w.x, w.y, w.z, S.w, obs[o], gmin);
+                    }
+                    if (hit) return HIT;
                 }
             }
+            if (GAP && n_obs > 0) tsafe = fminf(tsafe, (gmin - MMMP_GAP_SLACK) * inv_v);
         }
         if (flags & MMMP_CHECK_SELF) {
-            for (int t = 0; t < R.n_tables; ++t) {
-                const PairTableDev& P = R.table[t];
-                float qu = 0.f, qw = 0.f;
-#pragma unroll
-                for (int jj = 0; jj < MMMP_MAX_JOINTS; ++jj) {
-                    if (jj == P.joint_u) qu = qv[jj];
-                    if (jj == P.joint_v) qw = qv[jj];
-                }
-                int iu = (int)floorf((qu - P.lo_u) * P.inv_du);
-                int iv = (int)floorf((qw - P.lo_v) * P.inv_dv);
-                iu = min(max(iu, 0), P.n_u - 1);
-                iv = min(max(iv, 0), P.n_v - 1);
-                const int cell = iu * P.n_v + iv;
-                if ((__ldg(Wg->table_bits + P.word_offset + (cell >> 5)) >> (cell & 31)) & 1u) return true;
-            }
+            if (!skip_tables && tables_hit(Wg, R, lr, col, ql)) return HIT;
             for (int pi = 0; pi < R.n_self_pairs; ++pi) {
                 const uchar2 pr = R.self_pair[pi];
-                Affine TA, TB;
-                load_frame(TA, fr, stride, slot0, R.link_frame[pr.x]);
-                load_frame(TB, fr, stride, slot0, R.link_frame[pr.y]);
-                if (link_pair_hit(R, pr.x, TA, R, pr.y, TB)) return true;
+                const int fa = R.link_frame[pr.x], fb = R.link_frame[pr.y];
+                const float ra = R.link_bound[pr.x].w, rb = R.link_bound[pr.y].w;
+                const float dx = cl[(3 * pr.x + 0) * stride] - cl[(3 * pr.y + 0) * stride];
+                const float dy = cl[(3 * pr.x + 1) * stride] - cl[(3 * pr.y + 1) * stride];
+                const float dz = cl[(3 * pr.x + 2) * stride] - cl[(3 * pr.y + 2) * stride];
+                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                const float rr = ra + rb;
+                float g = INF, v = 0.f, want = 0.f;
+                if (GAP) {
+                    // relative travel of link b in link a's frame: joints fa .. fb-1 only
+#pragma unroll
+                    for (int m = 0; m < MMMP_MAX_JOINTS; ++m)
+                        if (m >= fa && m < fb) v = fmaf(adq[m], R.reach[m][fb], v);
+                    want = fmaf(v, t_want, MMMP_GAP_SLACK);
+                    g = fast_sqrt(d2) - rr;
+                }
+                if (GAP ? g <= want : d2 <= rr * rr) {
+                    Affine TA, TB;
+                    load_frame(TA, fr, stride, slot0, fa);
+                    load_frame(TB, fr, stride, slot0, fb);
+                    g = INF;
+                    if (link_pair_hit<GAP>(R, pr.x, TA, R, pr.y, TB, want, g)) return HIT;
+                }
+                if (GAP) tsafe = fminf(tsafe, __fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)));
             }
         }
     }
     if ((flags & MMMP_CHECK_ROBOTS) && n_r > 1) {
         for (int l1 = 0; l1 < n_r; ++l1) {
             const RobotDev& R1 = robs[l1];
+            const float* c1 = cen + (size_t)hdr->link_slot[l1] * 3 * stride;
             for (int l2 = l1 + 1; l2 < n_r; ++l2) {
                 const RobotDev& R2 = robs[l2];
+                const float* c2 = cen + (size_t)hdr->link_slot[l2] * 3 * stride;
                 for (int la = 0; la < R1.n_links; ++la) {
-                    if (R1.link_bound[la].w < 0.f) continue;
-                    Affine TA;
-                    load_frame(TA, fr, stride, hdr->frame_slot[l1], R1.link_frame[la]);
+                    const float ra = R1.link_bound[la].w;
+                    if (ra < 0.f) continue;
+                    const int fa = R1.link_frame[la];
+                    const float ax = c1[(3 * la + 0) * stride], ay = c1[(3 * la + 1) * stride],
+                                az = c1[(3 * la + 2) * stride];
                     for (int lb = 0; lb < R2.n_links; ++lb) {
-                        if (R2.link_bound[lb].w < 0.f) continue;
-                        if (R1.link_frame[la] == 0 && R2.link_frame[lb] == 0) continue;  // static pair
-                        Affine TB;
-                        load_frame(TB, fr, stride, hdr->frame_slot[l2], R2.link_frame[lb]);
-                        if (link_pair_hit(R1, la, TA, R2, lb, TB)) return true;
+                        const float rb = R2.link_bound[lb].w;
+                        if (rb < 0.f) continue;
+                        const int fb = R2.link_frame[lb];
+                        if (fa == 0 && fb == 0) continue;  // static pair
+                        const float dx = ax - c2[(3 * lb + 0) * stride], dy = ay - c2[(3 * lb + 1) * stride],
+                                    dz = az - c2[(3 * lb + 2) * stride];
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        const float rr = ra + rb;
+                        float g = INF, v = 0.f, want = 0.f;
+                        if (GAP) {
+                            const float va = fa > 0 ? vel[(hdr->frame_slot[l1] + fa - 1) * stride] : 0.f;
+                            const float vb = fb > 0 ? vel[(hdr->frame_slot[l2] + fb - 1) * stride] : 0.f;
+                            v = va + vb;
+                            want = fmaf(v, t_want, MMMP_GAP_SLACK);
+                            g = fast_sqrt(d2) - rr;
+                        }
+                        if (GAP ? g <= want : d2 <= rr * rr) {
+                            Affine TA, TB;
+                            load_frame(TA, fr, stride, hdr->frame_slot[l1], fa);
+                            load_frame(TB, fr, stride, hdr->frame_slot[l2], fb);
+                            g = INF;
+                            if (link_pair_hit<GAP>(R1, la, TA, R2, lb, TB, want, g)) return HIT;
+                        }
+                        if (GAP) tsafe = fminf(tsafe, __fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)));
                     }
                 }
             }
         }
     }
-    return false;
+    if (!GAP) return 1.f;
+    return fmaxf(tsafe, 0.f);
+}
+
+template <class QL>
+__device__ __forceinline__ bool spatial_in_collision(const WorldDev* __restrict__ Wg, const SpatialSmem* hdr,
+                                                     const RobotDev* robs, const ObstacleDev* obs, uint32_t flags,
+                                                     float* fr, int stride, const QL& ql) {
+    return spatial_eval<QL, false>(Wg, hdr, robs, obs, flags, fr, stride, ql, false, 0.f) < 0.f;
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 collide_configs_kernel(SpatialArgs A, const float* __restrict__ q, int ld, int64_t N, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     SpatialSmem* hdr;
@@ -258,7 +394,7 @@ collide_configs_kernel(SpatialArgs A, const float* __restrict__ q, int ld, int64
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 collide_pairs_kernel(SpatialArgs A, const float* __restrict__ qa, const float* __restrict__ qb, int ld,
                      int64_t N, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -275,17 +411,12 @@ collide_pairs_kernel(SpatialArgs A, const float* __restrict__ qa, const float* _
     }
 }
 
-// Edge checks.  A warp is split into groups of L lanes; one group = one edge, lane g of the
-// group takes steps g*rounds + r in round r (every round spreads over the whole edge).  After
-// each round a warp ballot tells every group whether one of its steps collided: that edge is
-// decided (early exit) and its lanes idle until all groups of the warp are done.  L is chosen
-// on the host so that rounds * L wastes the fewest lanes (50 steps: L = 10 -> 3 edges per
-// warp, 5 rounds, 94 % lane use; consecutive edges of a k-NN table share their first node,
-// so the groups of a warp see similar configurations).  Verdict = OR over all steps =
-// reference semantics (decoupled_prm.py:855-863).
-__global__ void __launch_bounds__(128)
+// Exhaustive edge check: one warp per edge; lane l takes steps l*rounds + r in round r so that
+// every round spreads over the whole edge, warp-ballot early exit.  Verdict = OR over all
+// steps = reference semantics (decoupled_prm.py:855-863).
+__global__ void __launch_bounds__(128, 4)
 collide_edges_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base, int ld,
-                     const int32_t* __restrict__ edges, int64_t E, int n_steps, double step, int L,
+                     const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
                      uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     SpatialSmem* hdr;
@@ -297,46 +428,167 @@ collide_edges_kernel(SpatialArgs A, const float* __restrict__ qa_base, const flo
     const int stride = blockDim.x;
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
-    const int epw = 32 / L;                 // edges per warp
-    const int group = lane / L, gl = lane - group * L;
-    const bool in_group = group < epw;
-    const int rounds = (n_steps + L - 1) / L;
-    const unsigned gmask = in_group ? (((L == 32) ? 0xffffffffu : ((1u << L) - 1u)) << (group * L)) : 0u;
-    const int64_t warp_id = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
-    for (int64_t e0 = warp_id * epw; e0 < E; e0 += n_warps * epw) {
-        const int64_t e = e0 + group;
-        bool valid = in_group && e < E;
-        const float *pa = qa_base, *pb = qa_base;
-        bool blocked = false;   // empty neighbour slot: reported as blocked
-        if (valid) {
-            if (edges) {
-                const int ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
-                blocked = ia < 0 || ib < 0;
-                pa = qa_base + (int64_t)(blocked ? 0 : ia) * ld;
-                pb = qa_base + (int64_t)(blocked ? 0 : ib) * ld;
-            } else {
-                pa = qa_base + e * ld;
-                pb = qb_base + e * ld;
+    const int rounds = (n_steps + 31) >> 5;
+    for (int64_t e = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); e < E;
+         e += (int64_t)gridDim.x * warps_per_cta) {
+        const float *pa, *pb;
+        if (edges) {
+            const int ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
+            if (ia < 0 || ib < 0) {  // empty neighbour slot: reported as blocked
+                if (lane == 0) out[e] = 1;
+                continue;
             }
+            pa = qa_base + (int64_t)ia * ld;
+            pb = qa_base + (int64_t)ib * ld;
+        } else {
+            pa = qa_base + e * ld;
+            pb = qb_base + e * ld;
         }
-        bool done = blocked || !valid;
-        bool collided = blocked;
-        for (int r = 0; r < rounds; ++r) {
-            const int i = gl * rounds + r;
+        bool any = false;
+        for (int r = 0; r < rounds && !any; ++r) {
+            const int i = lane * rounds + r;
             bool hit = false;
-            if (!done && i < n_steps) {
+            if (i < n_steps) {
                 QEdge ql{pa, pb, (float)((double)i * step)};
                 hit = spatial_in_collision(A.W, hdr, robs, obs, A.flags, cs, stride, ql);
             }
-            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-            if (ballot & gmask) {
-                collided = true;
-                done = true;
-            }
-            if (__all_sync(0xffffffffu, done)) break;
+            any = __any_sync(0xffffffffu, hit);
         }
-        if (valid && gl == 0) out[e] = collided ? 1 : 0;
+        if (lane == 0) out[e] = any ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ int nth_set_bit(uint64_t m, int r) {
+    const uint32_t lo = (uint32_t)m;
+    const int c = __popc(lo);
+    if (r < c) return (int)__fns(lo, 0, r + 1);
+    return 32 + (int)__fns((uint32_t)(m >> 32), 0, r - c + 1);
+}
+
+// Edge check that evaluates a step only while nothing proves it free (n_steps <= 64).
+// A warp is cut into 32/L groups of L lanes; a group owns one edge at a time and keeps the
+// set of still undecided steps as a bit mask.  Each round every lane of the group evaluates
+// one undecided step (spread evenly over the mask); an evaluation that collides decides the
+// edge, one that does not clears the steps its clearance covers.  A group whose mask is
+// empty writes the verdict and takes the next edge of the warp's contiguous chunk, so slow
+// edges never stall the other groups.
+template <int L>
+__global__ void __launch_bounds__(128, 4)
+collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base,
+                              int ld, const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
+                              float want_scale, unsigned long long* __restrict__ stats,
+                              uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SpatialSmem* hdr;
+    RobotDev* robs;
+    ObstacleDev* obs;
+    float* frames;
+    stage_world(A, smem, hdr, robs, obs, frames);
+    float* cs = frames + threadIdx.x;
+    const int stride = blockDim.x;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int group = lane / L, gl = lane % L;
+    const unsigned gmask = ((L == 32) ? FULL : ((1u << L) - 1u)) << (group * L);
+    const unsigned leaders_below = (L == 32) ? 0u : (0x11111111u * (L == 4) + 0x01010101u * (L == 8) +
+                                                     0x00010001u * (L == 16)) & ((1u << (group * L)) - 1u);
+    const int warps_per_cta = blockDim.x >> 5;
+    const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
+    const int64_t warp_id = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int64_t chunk = (E + n_warps - 1) / n_warps;
+    int64_t next = warp_id * chunk;
+    const int64_t w_end = next + chunk < E ? next + chunk : E;
+    const uint64_t all_steps = n_steps >= 64 ? ~0ull : ((1ull << n_steps) - 1ull);
+    const float steps_per_t = (float)(0.999 / step);
+    const bool use_tables = (A.flags & MMMP_CHECK_SELF) && hdr->any_tables;
+
+    int64_t e = -1;
+    uint64_t mask = 0;
+    bool collided = false;
+    const float *pa = qa_base, *pb = qa_base;
+    unsigned n_evals = 0;
+    while (true) {
+        // ---- groups without undecided steps: write the verdict, take the next edge
+        const bool need = mask == 0;
+        if (need && e >= 0 && gl == 0) out[e] = collided ? 1 : 0;
+        const unsigned needb = __ballot_sync(FULL, need && gl == 0);
+        bool table_hit = false;
+        if (need) {
+            const int64_t cand = next + __popc(needb & leaders_below);
+            e = -1;
+            if (cand < w_end) {
+                e = cand;
+                collided = false;
+                mask = all_steps;
+                if (edges) {
+                    const int ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
+                    if (ia < 0 || ib < 0) {  // empty neighbour slot: reported as blocked
+                        collided = true;
+                        mask = 0;
+                    }
+                    pa = qa_base + (int64_t)(ia < 0 ? 0 : ia) * ld;
+                    pb = qa_base + (int64_t)(ib < 0 ? 0 : ib) * ld;
+                } else {
+                    pa = qa_base + e * ld;
+                    pb = qb_base + e * ld;
+                }
+                if (use_tables && mask) {  // pair tables depend on q alone: look every step up
+                    for (int i = gl; i < n_steps; i += L) {
+                        QEdge ql{pa, pb, (float)((double)i * step)};
+                        for (int lr = 0; lr < hdr->n_r; ++lr)
+                            table_hit |= tables_hit(A.W, robs[lr], lr, hdr->col[lr], ql);
+                    }
+                }
+            }
+        }
+        next += __popc(needb);
+        {
+            const unsigned tb = __ballot_sync(FULL, table_hit);
+            if (need && (tb & gmask)) {
+                collided = true;
+                mask = 0;
+            }
+        }
+        if (!__any_sync(FULL, e >= 0)) break;
+        // ---- one evaluation per lane
+        const int cnt = __popcll(mask);
+        const int rank = ((2 * gl + 1) * cnt) / (2 * L);
+        const bool act = cnt > 0 && (gl == 0 || rank != ((2 * gl - 1) * cnt) / (2 * L));
+        uint64_t cover = 0;
+        bool hit = false;
+        if (act) {
+            ++n_evals;
+            const int i = nth_set_bit(mask, rank);
+            QEdge ql{pa, pb, (float)((double)i * step)};
+            // what this lane can use: its share of the undecided steps, on either side
+            const float t_want = (float)(cnt / (2 * L) + 1) * want_scale;
+            const float ts = spatial_eval<QEdge, true>(A.W, hdr, robs, obs, A.flags, cs, stride, ql, true, t_want);
+            if (ts < 0.f) {
+                hit = true;
+            } else {
+                const int n = (int)fminf(ts * steps_per_t, 64.f);
+                const int lo = max(i - n, 0), hi = min(i + n, 63);
+                cover = (~0ull >> (63 - hi)) & (~0ull << lo);
+            }
+        }
+#pragma unroll
+        for (int off = L >> 1; off > 0; off >>= 1) cover |= __shfl_xor_sync(FULL, cover, off);
+        const unsigned hb = __ballot_sync(FULL, hit);
+        if (hb & gmask) {
+            collided = true;
+            mask = 0;
+        } else {
+            mask &= ~cover;
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) n_evals += __shfl_xor_sync(FULL, n_evals, off);
+        if (lane == 0) {
+            atomicAdd(stats + 1, (unsigned long long)n_evals);
+            const int64_t first = warp_id * chunk;
+            if (w_end > first) atomicAdd(stats, (unsigned long long)(w_end - first));
+        }
     }
 }
 
@@ -352,13 +604,16 @@ int fill_args(const mmmp_world* w, int robot, uint32_t flags, SpatialArgs& A) {
         A.robots[0] = robot;
         A.col[0] = 0;
         A.slots = H->robots[robot].n_joints;
+        A.links = H->robots[robot].n_links;
     } else {
         A.n_r = H->n_robots;
         A.slots = 0;
+        A.links = 0;
         for (int r = 0; r < H->n_robots; ++r) {
             A.robots[r] = r;
             A.col[r] = H->robots[r].dof_offset;
             A.slots += H->robots[r].n_joints;
+            A.links += H->robots[r].n_links;
         }
     }
     return MMMP_OK;
@@ -368,7 +623,7 @@ size_t smem_bytes(const mmmp_world* w, const SpatialArgs& A, int block) {
     size_t off = (sizeof(SpatialSmem) + 15) & ~(size_t)15;
     off += (sizeof(RobotDev) * A.n_r + 15) & ~(size_t)15;
     off += (sizeof(ObstacleDev) * w->spatial_h->n_obstacles + 15) & ~(size_t)15;
-    off += (size_t)A.slots * 12 * sizeof(float) * block;
+    off += (size_t)MMMP_COLUMN_FLOATS(A.slots, A.links) * sizeof(float) * block;
     return off;
 }
 
@@ -390,15 +645,33 @@ int pick_launch(K kernel, const mmmp_world* w, const SpatialArgs& A, int64_t wor
     int per_sm = 1;
     MMMP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t per_cta = work_items_per_cta_hint * (block / 128 > 0 ? 1 : 1);
-    int64_t want = (total_items + per_cta - 1) / per_cta;
+    int64_t want = (total_items + work_items_per_cta_hint - 1) / work_items_per_cta_hint;
     const int64_t resident = (int64_t)sms * per_sm;
     // persistent grid: a whole number of waves, never more CTAs than work
     grid = (int)(want < resident ? (want < 1 ? 1 : want) : resident);
     return MMMP_OK;
 }
 
+unsigned long long* g_edge_stats = nullptr;  // device counters, enabled by mmmp_edge_stats
+
 }  // namespace
+
+extern "C" int mmmp_edge_stats(int enable, unsigned long long* out2_h) {
+    if (enable && !g_edge_stats) {
+        MMMP_CUDA_TRY(cudaMalloc(&g_edge_stats, 2 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMemset(g_edge_stats, 0, 2 * sizeof(unsigned long long)));
+    }
+    if (out2_h && g_edge_stats) {
+        MMMP_CUDA_TRY(cudaDeviceSynchronize());
+        MMMP_CUDA_TRY(cudaMemcpy(out2_h, g_edge_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        MMMP_CUDA_TRY(cudaMemset(g_edge_stats, 0, 2 * sizeof(unsigned long long)));
+    }
+    if (!enable && g_edge_stats) {
+        cudaFree(g_edge_stats);
+        g_edge_stats = nullptr;
+    }
+    return MMMP_OK;
+}
 
 extern "C" int mmmp_planar_collide_configs(const mmmp_world* w, int arm, const double* q, int ld, int64_t N,
                                            uint32_t flags, uint8_t* out, void* stream);
@@ -440,6 +713,7 @@ extern "C" int mmmp_collide_robot_pairs(const mmmp_world* w, int ra, int rb, con
     A.robots[1] = rb;
     A.col[0] = A.col[1] = 0;
     A.slots = H->robots[ra].n_joints + H->robots[rb].n_joints;
+    A.links = H->robots[ra].n_links + H->robots[rb].n_links;
     int block, grid;
     size_t smem;
     int rc = pick_launch(collide_pairs_kernel, w, A, 128, N, block, smem, grid);
@@ -455,29 +729,27 @@ static int launch_edges(const mmmp_world* w, int robot, const float* qa, const f
                         uint8_t* out, void* stream) {
     if (n_steps < 1 || n_steps > 4096) return MMMP_ERR_ARG;
     SpatialArgs A;
-    int rc = fill_args(w, robot, flags, A);
+    int rc = fill_args(w, robot, flags & ~(uint32_t)MMMP_CHECK_EXHAUSTIVE, A);
     if (rc) return rc;
     int block, grid;
     size_t smem;
-    rc = pick_launch(collide_edges_kernel, w, A, 4, E, block, smem, grid);
-    if (rc) return rc;
-    // lanes per edge: minimise rounds / (edges per warp)
-    int L = 32;
-    {
-        const int cand[6] = {32, 16, 10, 8, 5, 4};
-        double best = 1e30;
-        for (int c = 0; c < 6; ++c) {
-            const int l = cand[c];
-            const double cost = (double)((n_steps + l - 1) / l) / (double)(32 / l);
-            if (cost < best - 1e-12) {
-                best = cost;
-                L = l;
-            }
-        }
+    if ((flags & MMMP_CHECK_EXHAUSTIVE) || n_steps > 64 || n_steps < 4 || !(step > 0.0)) {
+        rc = pick_launch(collide_edges_kernel, w, A, 4, E, block, smem, grid);
+        if (rc) return rc;
+        const int wpc = block / 32;
+        grid = mmmp_div_up(E, wpc) < grid ? mmmp_div_up(E, wpc) : grid;
+        MMMP_LAUNCH(collide_edges_kernel, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps, step, out);
+    } else {
+        constexpr int L = 4;
+        rc = pick_launch(collide_edges_adaptive_kernel<L>, w, A, 4 * (32 / L) * 8, E, block, smem, grid);
+        if (rc) return rc;
+        // clearance a lane asks for = (its share of the undecided steps) * step * refine
+        double refine = 1.0;
+        if (const char* s = getenv("MMMP_EDGE_REFINE")) refine = atof(s);
+        const float want_scale = (float)(step / 0.999 * refine);
+        MMMP_LAUNCH(collide_edges_adaptive_kernel<L>, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps,
+                    step, want_scale, g_edge_stats, out);
     }
-    const int wpc = block / 32 * (32 / L);  // edges per CTA pass
-    grid = mmmp_div_up(E, wpc) < grid ? mmmp_div_up(E, wpc) : grid;
-    MMMP_LAUNCH(collide_edges_kernel, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps, step, L, out);
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }

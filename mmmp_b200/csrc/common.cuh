@@ -48,6 +48,7 @@ struct RobotDev {
     int link_frame[MMMP_MAX_LINKS];              // non-decreasing in the link id
     int frame_link_begin[MMMP_MAX_JOINTS + 2];   // links of frame f: [begin[f], begin[f+1])
     int link_sphere_begin[MMMP_MAX_LINKS + 1];
+    float reach[MMMP_MAX_JOINTS][MMMP_MAX_JOINTS + 1];  // [m][f]: bound of |d centre / d q_m|, frame f
     uchar2 self_pair[MMMP_MAX_SELF_PAIRS];
     PairTableDev table[MMMP_MAX_PAIR_TABLES];
     float4 sphere[MMMP_MAX_SPHERES];    // frame local xyz, r (frame-0 links: WORLD xyz)

@@ -4,18 +4,25 @@
 #pragma once
 #include "common.cuh"
 
-__device__ __forceinline__ bool sphere_hits_obstacle(float cx, float cy, float cz, float r,
-                                                     const ObstacleDev& O) {
+// Returns the overlap verdict.  With GAP the sphere's clearance from the primitive (distance
+// between the surfaces, meaningful when there is no overlap) is folded into `gap` by min; the
+// verdict is computed by the same expressions either way.
+template <bool GAP>
+__device__ __forceinline__ bool sphere_vs_obstacle(float cx, float cy, float cz, float r, const ObstacleDev& O,
+                                                   float& gap) {
     const float* p = O.p;
     switch (O.type) {
         case MMMP_OBS_PLANE: {
             const float sd = fmaf(p[0], cx, fmaf(p[1], cy, p[2] * cz)) - p[3];
+            if (GAP) gap = fminf(gap, sd - r);
             return sd <= r;
         }
         case MMMP_OBS_SPHERE: {
             const float dx = cx - p[0], dy = cy - p[1], dz = cz - p[2];
             const float rr = r + p[3];
-            return fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            if (GAP) gap = fminf(gap, sqrtf(d2) - rr);
+            return d2 <= rr * rr;
         }
         case MMMP_OBS_BOX: {
             const float dx = cx - p[0], dy = cy - p[1], dz = cz - p[2];
@@ -26,7 +33,9 @@ __device__ __forceinline__ bool sphere_hits_obstacle(float cx, float cy, float c
             const float ex = fmaxf(fabsf(bx) - p[3], 0.f);
             const float ey = fmaxf(fabsf(by) - p[4], 0.f);
             const float ez = fmaxf(fabsf(bz) - p[5], 0.f);
-            return fmaf(ex, ex, fmaf(ey, ey, ez * ez)) <= r * r;
+            const float e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+            if (GAP) gap = fminf(gap, sqrtf(e2) - r);
+            return e2 <= r * r;
         }
         case MMMP_OBS_CYLINDER: {
             const float dx = cx - p[0], dy = cy - p[1], dz = cz - p[2];
@@ -35,8 +44,16 @@ __device__ __forceinline__ bool sphere_hits_obstacle(float cx, float cy, float c
             const float rad = sqrtf(fmaxf(d2 - h * h, 0.f));
             const float eh = fmaxf(fabsf(h) - p[6], 0.f);
             const float er = fmaxf(rad - p[7], 0.f);
-            return fmaf(eh, eh, er * er) <= r * r;
+            const float e2 = fmaf(eh, eh, er * er);
+            if (GAP) gap = fminf(gap, sqrtf(e2) - r);
+            return e2 <= r * r;
         }
     }
     return false;
+}
+
+__device__ __forceinline__ bool sphere_hits_obstacle(float cx, float cy, float cz, float r,
+                                                     const ObstacleDev& O) {
+    float unused = 0.f;
+    return sphere_vs_obstacle<false>(cx, cy, cz, r, O, unused);
 }

@@ -149,6 +149,40 @@ extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
                             &R.link_bound[l]);
             if (R.link_frame[l] != 0) R.n_moving_links++;
         }
+        // reach[m][f]: lever arm of joint m over the sphere centres of frame f (f > m), an upper
+        // bound of |d centre / d q_m| over ALL configurations.  Enclose the centres of frame f in
+        // a ball, then walk towards the base: seen from frame m+1 the ball may be anywhere on
+        // its circle about that frame's z axis (= joint m's axis), so lever = |xy| + rho; the
+        // swept set is enclosed by the ball centred on the axis, which the joint origin maps
+        // into the next frame down.
+        for (int m = 0; m < MMMP_MAX_JOINTS; ++m)
+            for (int f = 0; f <= MMMP_MAX_JOINTS; ++f) R.reach[m][f] = 0.f;
+        for (int f = 1; f <= d.n_joints; ++f) {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            int cnt = 0;
+            for (int s = 0; s < d.n_spheres; ++s) {
+                if (d.link_frame[d.sphere_link[s]] != f) continue;
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = std::min(lo[k], d.sphere[s][k]);
+                    hi[k] = std::max(hi[k], d.sphere[s][k]);
+                }
+                ++cnt;
+            }
+            if (!cnt) continue;
+            double b[3] = {(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2}, rho = 0;
+            for (int s = 0; s < d.n_spheres; ++s) {
+                if (d.link_frame[d.sphere_link[s]] != f) continue;
+                const double dx = d.sphere[s][0] - b[0], dy = d.sphere[s][1] - b[1], dz = d.sphere[s][2] - b[2];
+                rho = std::max(rho, std::sqrt(dx * dx + dy * dy + dz * dz));
+            }
+            for (int m = f - 1; m >= 0; --m) {
+                const double arm = std::sqrt(b[0] * b[0] + b[1] * b[1]);
+                R.reach[m][f] = (float)((arm + rho) * (1.0 + 1e-5) + 1e-7);
+                const double axis_pt[3] = {0.0, 0.0, b[2]};
+                rho += arm;
+                affine_point_d(d.origin[m], axis_pt, b);
+            }
+        }
         // exact pair tables (deduplicated across robots by content)
         unsigned int table_mask[MMMP_MAX_LINKS];
         for (int l = 0; l < MMMP_MAX_LINKS; ++l) table_mask[l] = 0;

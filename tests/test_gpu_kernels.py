@@ -205,6 +205,41 @@ def test_panda_edges_vs_sphere_oracle(core, panda_model, cuda):
     assert _np(w.collide_edges(allq, e, 50, 0.02, 0, F)).tolist() == [1, 1]
 
 
+def test_edge_step_skipping_keeps_every_verdict(core, panda_model, cuda):
+    """The default edge kernel skips interpolation steps a clearance bound proves free; its
+    verdicts must equal the exhaustive kernel's (every step evaluated) bit for bit."""
+    from mmmp_b200._lib import CHECK_EXHAUSTIVE, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_SELF
+    rng = np.random.default_rng(21)
+    base = core.base_matrix((0, 0, 0.01))
+    n = 30000
+    qa = np.round(rng.uniform(LIMITS[:, 0], LIMITS[:, 1], (n, 7)), 2)
+    sigma = rng.choice([0.02, 0.1, 0.3, 1.0], size=(n, 1))     # short roadmap edges up to long ones
+    qb = np.clip(np.round(qa + rng.normal(0, 1.0, qa.shape) * sigma, 2), LIMITS[:, 0], LIMITS[:, 1])
+    qb[:50] = qa[:50]                                            # degenerate edges
+    a32, b32 = core.pack_f32(core.to_device_f64(qa)), core.pack_f32(core.to_device_f64(qb))
+    for obs in (_scene(core), [core.plane((0, 0, 1), 0.0)], []):
+        w = core.SpatialWorld([core.RobotSpec(panda_model, base)], obs)
+        for flags in (CHECK_SELF, CHECK_OBSTACLES, CHECK_SELF | CHECK_OBSTACLES):
+            for n_steps, step in ((50, 0.02), (64, 1.0 / 64), (20, 0.05), (5, 0.2)):
+                fast = _np(w.collide_segments(a32, b32, n_steps, step, 0, flags))
+                full = _np(w.collide_segments(a32, b32, n_steps, step, 0, flags | CHECK_EXHAUSTIVE))
+                assert (fast == full).all(), (len(obs), flags, n_steps, int((fast != full).sum()))
+        assert 0.02 < full.mean() < 0.98
+    # composite rows of two robots, robot-robot pairs included
+    bases = [core.base_matrix((-0.35, 0, 0.01)), core.base_matrix((0.35, 0, 0.01), (0, 0, 1, 0))]
+    w2 = core.SpatialWorld([core.RobotSpec(panda_model, bases[0], 0), core.RobotSpec(panda_model, bases[1], 7)],
+                           [core.plane((0, 0, 1), 0.0)])
+    m = 6000
+    ca = np.concatenate([qa[:m], qa[m:2 * m]], 1)
+    cb = np.concatenate([qb[:m], qb[m:2 * m]], 1)
+    ca32, cb32 = core.pack_f32(core.to_device_f64(ca)), core.pack_f32(core.to_device_f64(cb))
+    for flags in (CHECK_ROBOTS, CHECK_SELF | CHECK_OBSTACLES | CHECK_ROBOTS):
+        fast = _np(w2.collide_segments(ca32, cb32, 50, 0.02, -1, flags))
+        full = _np(w2.collide_segments(ca32, cb32, 50, 0.02, -1, flags | CHECK_EXHAUSTIVE))
+        assert (fast == full).all(), (flags, int((fast != full).sum()))
+        assert 0.02 < full.mean() < 0.98
+
+
 def test_two_pandas_composite_and_pairs_vs_sphere_oracle(core, panda_model, cuda):
     from mmmp_b200._lib import CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_SELF
     from oracle.spheres import SphereChecker

@@ -52,4 +52,6 @@ eh = timed("collide_edges 50 steps", lambda: world.collide_edges(free32, edges, 
 print("edge collision rate", float(eh.float().mean()), "ambiguous", float(amb.float().mean()))
 timed("collide_edges (self only)", lambda: world.collide_edges(free32, edges, 50, 0.02, 0, CHECK_SELF))
 timed("collide_edges (obst only)", lambda: world.collide_edges(free32, edges, 50, 0.02, 0, CHECK_OBSTACLES))
+eh2 = timed("collide_edges exhaustive", lambda: world.collide_edges(free32, edges, 50, 0.02, 0, F | 16))
+print("verdict mismatches vs exhaustive", int((eh2 != eh).sum()))
 fk = timed("fk_chain", lambda: world.fk(free32, 0))
