@@ -267,10 +267,11 @@ int mmmp_knn(const float* fref_d, const float* xref_d, int64_t n_ref,
              int exclude_self, int causal, int64_t query_id0, int32_t* out_idx_d,
              float* out_dist_d, void* stream);
 
-/* profiling aid: enable != 0 turns on four device counters of the scan kernel
- * (exact evaluations, list insertions, warp drains, tiles loaded); out4_h (may
- * be NULL) receives and resets them; enable == 0 frees them.                 */
-int mmmp_knn_stats(int enable, unsigned long long* out4_h);
+/* profiling aid: enable != 0 turns on five device counters of the scan kernel
+ * (exact evaluations, list insertions, warp drains, tiles loaded, most tiles
+ * loaded by one CTA); out5_h (may be NULL) receives and resets them;
+ * enable == 0 frees them.                                                   */
+int mmmp_knn_stats(int enable, unsigned long long* out5_h);
 
 /* Re-rank candidates in fp64 with the reference's own arithmetic order:
  * cand_idx_d [n_query, kc] (from mmmp_knn with kc >= k) -> out [n_query, k]

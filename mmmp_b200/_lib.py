@@ -128,6 +128,8 @@ SIGNATURES = {
 _RESTYPES = {"mmmp_launch_count": C.c_int64}
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmmmp_b200.so")
+if os.environ.get("MMMP_B200_LIB"):    # kernel-tuning builds of the same library (tools/build_variant.py)
+    LIB_PATH = os.path.abspath(os.environ["MMMP_B200_LIB"])
 _lib = None
 
 

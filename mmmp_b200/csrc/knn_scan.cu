@@ -9,25 +9,29 @@
 //       centroid sum_g w_g p_g (3 floats) -- triangle inequality
 //       sum_g w_g |dp_g| >= | sum_g w_g dp_g |.
 // A pack kernel lays the filter rows out as [x_0 .. x_{d-1}, 0 .., B_r] (B_r in the last of
-// W = 4/8/16/32 columns), so the loop needs nothing but the row itself.
+// W = 4/8/16/32 columns) and the exact rows as [x_0 .. x_{dim-1}] with an ODD row stride S,
+// both in the scan order, so that a tile of either is one contiguous block.
 //
 // Spatial ordering + exact tile culling (non-causal searches with >= 4096 references):
 // rows are counting-sorted by the Morton code of their grid cell (first three filter
-// dimensions), so that a shared-memory tile of 256 consecutive rows and a CTA's 128*Q
+// dimensions), so that a shared-memory tile of 128 consecutive rows and a CTA's 128*Q
 // consecutive queries are both spatially compact; every tile carries its bounding box.
-// The producer walks the tiles outward from the CTA's own position and only loads a
-// tile whose box is closer to the CTA's query box than the CTA's current worst k-th
-// best bound -- a tile that is skipped cannot contain a neighbour, so the result is
-// identical to the exhaustive scan (which remains the path for causal / small searches).
+// The producer warp walks the tiles outward from the CTA's own position, 32 boxes per
+// step, and only loads a tile whose box is closer to the CTA's query box than the CTA's
+// current worst k-th best bound -- a tile that is skipped cannot contain a neighbour, so
+// the result is identical to the exhaustive scan (which remains the path for causal /
+// small searches).
 //
 // CTA = 4 consumer warps + 1 producer warp (warp specialisation).  The producer streams
-// packed reference rows L2/HBM -> shared memory with the TMA engine (cp.async.bulk, 4-stage
-// ring, full/empty mbarriers); consumer warps never meet at a CTA barrier.  Every
-// consumer thread owns Q queries in registers and reads the tile rows as shared-memory
-// broadcasts (LDS.128), 4 rows per step, software pipelined.  Pairs that pass the filter
-// are appended to a small per-thread queue in shared memory; when any lane's queue is
-// nearly full the warp drains it: exact fp32 metric on the "exact rows" (read from
-// L2/HBM) and sorted insertion into the thread's candidate column, which tightens the
+// the filter rows AND the exact rows of a tile L2/HBM -> shared memory with the TMA engine
+// (cp.async.bulk, 3-stage ring, full/empty mbarriers); consumer warps never meet at a CTA
+// barrier.  Every consumer thread owns Q queries (filter form in registers, exact row in a
+// shared-memory column) and reads the tile's filter rows as shared-memory broadcasts
+// (LDS.128), 4 rows per step, software pipelined.  Pairs that pass the filter are appended
+// to a small per-thread byte queue; the warp drains the queues when one is nearly full and
+// at the end of every tile: exact fp32 metric against the tile's exact rows -- still
+// resident in shared memory (odd stride: conflict free), so the drain never waits on a
+// gather -- and sorted insertion into the thread's candidate column, which tightens the
 // thread's threshold.
 //
 // Reference call sites replaced: the heap loops of
@@ -42,11 +46,21 @@ namespace {
 constexpr int KNN_CWARPS = 4;                  // consumer warps per CTA
 constexpr int KNN_CTHREADS = KNN_CWARPS * 32;  // consumer threads
 constexpr int KNN_THREADS = KNN_CTHREADS + 32; // + producer warp
-constexpr int KNN_STAGES = 4;
-constexpr int KNN_TILE = 256;                  // reference rows per shared-memory tile
-constexpr int KNN_RU = 4;                      // rows per inner-loop step
-constexpr int KNN_QSLACK = 16;                 // queue entries a thread may hold before its warp drains
-__host__ __device__ constexpr int knn_qcap(int Q) { return KNN_RU * Q + KNN_QSLACK; }
+#ifndef MMMP_KNN_STAGES
+#define MMMP_KNN_STAGES 2
+#endif
+#ifndef MMMP_KNN_DU
+#define MMMP_KNN_DU 1
+#endif
+constexpr int KNN_STAGES = MMMP_KNN_STAGES;
+constexpr int KNN_DU = MMMP_KNN_DU;            // drain: exact evaluations in flight per lane
+constexpr int KNN_TILE = 128;                  // reference rows per shared-memory tile
+#ifndef MMMP_KNN_RU
+#define MMMP_KNN_RU 8
+#endif
+constexpr int KNN_RU = MMMP_KNN_RU;            // rows per inner-loop step
+constexpr int KNN_QSLACK = 12;                 // queue entries a thread may hold before its warp drains
+constexpr int KNN_QC = KNN_RU + KNN_QSLACK;    // queue capacity per (thread, query)
 constexpr float KNN_SLACK = 2.0e-5f;           // relative slack of the fp32 filter
 constexpr int KNN_CULL_MIN = 4096;             // references below which sorting does not pay
 
@@ -162,8 +176,8 @@ cell_scatter_kernel(const uint32_t* __restrict__ keys, int64_t n, const int64_t*
     }
 }
 
-// ---- filter-row packing -----------------------------------------------------------------
-// out[p] = [in[perm[p]][0..d), 0 .., (1 - eps) * |.|^2]   (W columns); perm may be NULL
+// ---- row packing ----------------------------------------------------------------------
+// filter rows: out[p] = [in[perm[p]][0..d), 0 .., (1 - eps) * |.|^2]   (W columns); perm may be NULL
 __global__ void __launch_bounds__(256)
 knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, const int32_t* __restrict__ perm,
                 float* __restrict__ out, int W) {
@@ -180,15 +194,30 @@ knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, const
     }
 }
 
-// per-tile bounding boxes of the packed (sorted) rows: boxes[t] = {lo0,lo1,lo2,hi0,hi1,hi2}
+// exact rows in scan order with row stride S: out[p] = in[perm[p]][0..S) (zero beyond `dim`);
+// rows n .. n_pad-1 (the tail a partial tile's bulk copy touches) are zeroed
 __global__ void __launch_bounds__(256)
+knn_pack_exact_kernel(const float* __restrict__ in, int ld_in, int dim, int64_t n, int64_t n_pad,
+                      const int32_t* __restrict__ perm, float* __restrict__ out, int S) {
+    const int64_t total = n_pad * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / S;
+        const int c = (int)(e - p * S);
+        float v = 0.f;
+        if (p < n && c < dim) v = in[(int64_t)(perm ? perm[p] : p) * ld_in + c];
+        out[e] = v;
+    }
+}
+
+// per-tile bounding boxes of the packed (sorted) rows: boxes[t] = {lo0,lo1,lo2,hi0,hi1,hi2}
+__global__ void __launch_bounds__(KNN_TILE)
 tile_box_kernel(const float* __restrict__ packed, int W, int nd, int64_t n, float* __restrict__ boxes) {
     const int64_t t = blockIdx.x;
     const int64_t r = t * KNN_TILE + threadIdx.x;
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     if (r < n)
         for (int c = 0; c < nd; ++c) lo[c] = hi[c] = packed[r * W + c];
-    __shared__ float s[6][8];
+    __shared__ float s[6][KNN_TILE / 32];
     for (int c = 0; c < 3; ++c) {
         for (int o = 16; o > 0; o >>= 1) {
             lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
@@ -202,41 +231,49 @@ tile_box_kernel(const float* __restrict__ packed, int W, int nd, int64_t n, floa
     __syncthreads();
     if (threadIdx.x < 6) {
         float v = s[threadIdx.x][0];
-        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, s[threadIdx.x][w]) : fmaxf(v, s[threadIdx.x][w]);
+        for (int w = 1; w < KNN_TILE / 32; ++w)
+            v = threadIdx.x < 3 ? fminf(v, s[threadIdx.x][w]) : fmaxf(v, s[threadIdx.x][w]);
         if (threadIdx.x % 3 >= nd) v = 0.f;
         boxes[t * 6 + threadIdx.x] = v;
     }
 }
 
 struct KnnArgs {
-    const float* pref;     // packed filter rows of the references [n_ref, W] (sorted when perm != NULL)
-    const float* pquery;   // packed filter rows of the queries [n_query, W] (sorted when qperm != NULL)
-    const float* xref;     // exact rows [n_ref, ldx], original order
-    const float* xquery;   // exact rows [n_query, ldx], original order
-    const int32_t* perm;   // sorted position -> original reference row (NULL: identity)
-    const int32_t* qperm;  // sorted position -> original query row (NULL: identity)
+    const float* pref;     // packed filter rows of the references [n_ref, W], scan order
+    const float* pquery;   // packed filter rows of the queries [n_query, W], scan order
+    const float* xs;       // exact rows of the references [n_ref rounded up to 4, S], scan order
+    const float* xquery;   // exact rows of the queries [n_query, ldx], original order
+    const int32_t* perm;   // scan position -> original reference row (NULL: identity)
+    const int32_t* qperm;  // scan position -> original query row (NULL: identity)
     const float* boxes;    // per-tile bounding boxes (NULL: no culling)
     int64_t n_ref, n_query, query_id0;
-    int ldx, kc, flags;    // flags: 1 = exclude self, 2 = causal
+    int ldx, S, kc;
+    int flags;             // 1 = exclude self, 2 = causal, 4 = queries ARE the references (same scan order)
     int tiles_per_split, n_splits;
     int32_t* out_idx;      // [n_query, n_splits, kc]
     float* out_val;        // candidate-list domain (L2/SQ_SUM: squared ; GROUP: distance)
-    unsigned long long* stats;  // optional: [0] exact evaluations, [1] insertions, [2] drains, [3] tiles loaded
+    unsigned long long* stats;  // optional: [0] exact evaluations, [1] insertions, [2] drains, [3] tiles loaded, [4] most tiles loaded by one CTA
     MetricDev M;
 };
 
-// exact fp32 metric in the candidate list's domain
-__device__ __forceinline__ float exact_metric(const MetricDev& M, const float* __restrict__ a,
-                                              const float* __restrict__ b) {
+// exact fp32 metric in the candidate list's domain: a = query row in a shared-memory column
+// (element stride `as`), b = reference row in the shared-memory tile (contiguous)
+__device__ __forceinline__ float exact_metric(const MetricDev& M, const float* a, int as, const float* b) {
     float v = 0.f;
     if (M.kind == MMMP_METRIC_GROUP_L2_SUM) {
-        for (int g = 0; g < M.n_groups; ++g) {
-            const float dx = a[3 * g] - b[3 * g], dy = a[3 * g + 1] - b[3 * g + 1], dz = a[3 * g + 2] - b[3 * g + 2];
-            v = fmaf(M.w[g], sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz))), v);
+#pragma unroll
+        for (int g = 0; g < MMMP_MAX_GROUPS; ++g) {
+            if (g < M.n_groups) {
+                const float dx = a[(3 * g) * as] - b[3 * g], dy = a[(3 * g + 1) * as] - b[3 * g + 1],
+                            dz = a[(3 * g + 2) * as] - b[3 * g + 2];
+                const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                v = fmaf(M.w[g], s2 * rsqrtf(fmaxf(s2, 1e-30f)), v);  // candidates are re-ranked in fp64
+            }
         }
     } else {
+#pragma unroll 4
         for (int i = 0; i < M.dim; ++i) {
-            const float d = a[i] - b[i];
+            const float d = a[i * as] - b[i];
             v = fmaf(d, d, v);
         }
     }
@@ -257,34 +294,43 @@ struct ScanCtl {                  // per-CTA control block in shared memory
     float wbox[KNN_CWARPS][6];    // query box of every consumer warp
     volatile float wtau[KNN_CWARPS];  // worst (largest) filter-domain bound of every consumer warp
     volatile int tile_id[KNN_STAGES];
+    int pre[KNN_CWARPS][33];      // drain: exclusive prefix of the lanes' queue lengths
 };
 
+// shared-memory layout (floats unless noted), LS = KNN_CTHREADS * Q:
+//   ring[STAGES][ TILE*W filter | TILE*S exact ]  lv[kc][LS]  li[kc][LS]  xq[S][LS]
+//   qval[Q][QC][CTHREADS]   queue (bytes) [Q][QC][CTHREADS]   bars[2*STAGES] (u64)   ctl
+__host__ __device__ constexpr size_t knn_stage_floats(int W, int S) { return (size_t)KNN_TILE * (W + S); }
+__host__ __device__ constexpr size_t knn_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 template <int F4, int Q>
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, F4 <= 2 ? 3 : 1)
 knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int W = F4 * 4;
     constexpr int LS = KNN_CTHREADS * Q;  // column stride of the per-query shared arrays
-    constexpr int QCAP = knn_qcap(Q);
-    // layout: tiles[STAGES][TILE][W] | lv[kc][LS] | li[kc][LS] | queue[QCAP][CTHREADS] | full[] empty[] | ctl
-    float* tiles = reinterpret_cast<float*>(smem_raw);
-    float* lv = tiles + KNN_STAGES * KNN_TILE * W;
-    int* li = reinterpret_cast<int*>(lv + (size_t)A.kc * LS);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(li + (size_t)A.kc * LS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(queue + QCAP * KNN_CTHREADS);
+    const int S = A.S;
+    const int kc = A.kc;
+    const size_t stage_floats = knn_stage_floats(W, S);
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    float* lv = ring + KNN_STAGES * stage_floats;
+    int* li = reinterpret_cast<int*>(lv + (size_t)kc * LS);
+    float* xq = reinterpret_cast<float*>(li + (size_t)kc * LS);
+    float* qval = xq + (size_t)S * LS;
+    unsigned char* queue = reinterpret_cast<unsigned char*>(qval + (size_t)Q * KNN_QC * KNN_CTHREADS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + knn_align((size_t)(queue - smem_raw) +
+                                                                      (size_t)Q * KNN_QC * KNN_CTHREADS, 8));
     ScanCtl* ctl = reinterpret_cast<ScanCtl*>(bars + 2 * KNN_STAGES);
-    const uint32_t tiles_s = smem_u32(tiles);
+    const uint32_t ring_s = smem_u32(ring);
     const uint32_t full_s = smem_u32(bars), empty_s = smem_u32(bars + KNN_STAGES);
 
     const int tid = threadIdx.x;
-    const int kc = A.kc;
     const bool cull = A.boxes != nullptr;
     if (tid == 0) {
         for (int s = 0; s < KNN_STAGES; ++s) {
             mbar_init(full_s + 8 * s, 1);
             mbar_init(empty_s + 8 * s, KNN_CWARPS);
         }
-        for (int w = 0; w < KNN_CWARPS; ++w) ctl->wtau[w] = CUDART_INF_F;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -300,14 +346,17 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     int64_t tile_hi = tile_lo + A.tiles_per_split;
     if (tile_hi > total_tiles) tile_hi = total_tiles;
 
-    // ---- queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q) ----
+    // ---- queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q),
+    //      exact row in this thread's shared-memory column ----
     float a2[Q][W - 1], thr[Q], Aq[Q], tauf[Q];
+    int64_t qrow[Q];
     if (tid < KNN_CTHREADS) {
         float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
         for (int qq = 0; qq < Q; ++qq) {
             const int64_t qi = q_first + qq * KNN_CTHREADS + tid;
             const bool valid = qi < A.n_query;
+            const int col = qq * KNN_CTHREADS + tid;
 #pragma unroll
             for (int i = 0; i < W - 1; ++i) {
                 const float v = valid ? __ldg(A.pquery + qi * W + i) : 0.f;
@@ -320,9 +369,12 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             Aq[qq] = valid ? __ldg(A.pquery + qi * W + (W - 1)) : 0.f;
             thr[qq] = valid ? CUDART_INF_F : -CUDART_INF_F;
             tauf[qq] = valid ? CUDART_INF_F : 0.f;
+            qrow[qq] = valid ? (A.qperm ? (int64_t)__ldg(A.qperm + qi) : qi) : 0;
+            for (int c = 0; c < S; ++c)
+                xq[c * LS + col] = (valid && c < A.M.dim) ? __ldg(A.xquery + qrow[qq] * A.ldx + c) : 0.f;
             for (int c = 0; c < kc; ++c) {
-                lv[c * LS + qq * KNN_CTHREADS + tid] = CUDART_INF_F;
-                li[c * LS + qq * KNN_CTHREADS + tid] = 0x7fffffff;
+                lv[c * LS + col] = CUDART_INF_F;
+                li[c * LS + col] = 0x7fffffff;
             }
         }
 #pragma unroll
@@ -337,23 +389,23 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                 ctl->wbox[tid >> 5][3 + c] = (W - 1 > c) ? hi[c] : 0.f;
             }
         }
+        // a warp without a single valid query must not hold the CTA's culling bound at infinity
+        float w0 = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) w0 = fmaxf(w0, tauf[qq]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w0 = fmaxf(w0, __shfl_xor_sync(0xffffffffu, w0, o));
+        if ((tid & 31) == 0) ctl->wtau[tid >> 5] = w0;
     }
     __syncthreads();
 
     if (tid >= KNN_CTHREADS) {
-        // ================= producer warp: one elected lane drives the TMA ring =================
-        if (tid == KNN_CTHREADS) {
-            float cbox[6];
-            for (int c = 0; c < 3; ++c) {
-                cbox[c] = CUDART_INF_F;
-                cbox[3 + c] = -CUDART_INF_F;
-                for (int w = 0; w < KNN_CWARPS; ++w) {
-                    cbox[c] = fminf(cbox[c], ctl->wbox[w][c]);
-                    cbox[3 + c] = fmaxf(cbox[3 + c], ctl->wbox[w][3 + c]);
-                }
-            }
-            int slot = 0;
-            auto push = [&](int64_t t) {  // t < 0: end marker
+        // ================= producer warp: lane 0 drives the TMA ring =================
+        const int lane = tid & 31;
+        int slot = 0;
+        unsigned long long loaded = 0;
+        auto push = [&](int64_t t) {  // t < 0: end marker
+            if (lane == 0) {
                 const int s = slot % KNN_STAGES;
                 mbar_wait(empty_s + 8 * s, ((slot / KNN_STAGES) & 1) ^ 1);
                 ctl->tile_id[s] = (int)t;
@@ -363,107 +415,167 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     const int64_t r0 = t * KNN_TILE;
                     int64_t cnt = ref_end - r0;
                     if (cnt > KNN_TILE) cnt = KNN_TILE;
-                    const uint32_t bytes = (uint32_t)(cnt * W * sizeof(float));
-                    mbar_expect_tx(full_s + 8 * s, bytes);
-                    tma_load_1d(tiles_s + (uint32_t)s * KNN_TILE * W * 4, A.pref + r0 * W, bytes, full_s + 8 * s);
+                    const uint32_t fbytes = (uint32_t)(cnt * W * sizeof(float));
+                    const uint32_t xbytes = (uint32_t)(((cnt + 3) & ~(int64_t)3) * S * sizeof(float));
+                    const uint32_t dst = ring_s + (uint32_t)(s * stage_floats * sizeof(float));
+                    mbar_expect_tx(full_s + 8 * s, fbytes + xbytes);
+                    tma_load_1d(dst, A.pref + r0 * W, fbytes, full_s + 8 * s);
+                    tma_load_1d(dst + KNN_TILE * W * 4, A.xs + r0 * S, xbytes, full_s + 8 * s);
+                    ++loaded;
                 }
-                ++slot;
-            };
-            if (!cull) {
-                for (int64_t t = tile_lo; t < tile_hi; ++t) push(t);
-            } else {
-                // outward walk from the tile that holds this CTA's own rows (queries and references
-                // share the spatial order); a tile is loaded only if it can still matter
-                int64_t centre = (int64_t)((double)(q_first + LS / 2) / (double)(A.n_query > 0 ? A.n_query : 1) *
-                                           (double)total_tiles);
-                if (centre < tile_lo) centre = tile_lo;
-                if (centre >= tile_hi) centre = tile_hi - 1;
-                int64_t up = centre, down = centre - 1;
-                unsigned long long loaded = 0;
-                while (up < tile_hi || down >= tile_lo) {
-                    for (int side = 0; side < 2; ++side) {
-                        int64_t t;
-                        if (side == 0) {
-                            if (up >= tile_hi) continue;
-                            t = up++;
-                        } else {
-                            if (down < tile_lo) continue;
-                            t = down--;
-                        }
-                        float worst = 0.f;
-                        for (int w = 0; w < KNN_CWARPS; ++w) worst = fmaxf(worst, ctl->wtau[w]);
-                        const float d2 = box_dist2(cbox, A.boxes + t * 6);
-                        if (d2 > worst * (1.f + 1e-4f) + 1e-12f) continue;  // cannot hold a neighbour
-                        push(t);
-                        ++loaded;
-                    }
-                }
-                if (A.stats) atomicAdd(A.stats + 3, loaded);
             }
-            push(-1);
+            ++slot;
+            __syncwarp();
+        };
+        if (!cull) {
+            for (int64_t t = tile_lo; t < tile_hi; ++t) push(t);
+        } else {
+            // outward walk from the tile that holds this CTA's own rows (queries and references
+            // share the spatial order), 16 boxes per side and step; a tile is loaded only if it
+            // can still matter when its turn comes
+            float cbox[6];
+            for (int c = 0; c < 3; ++c) {
+                cbox[c] = CUDART_INF_F;
+                cbox[3 + c] = -CUDART_INF_F;
+                for (int w = 0; w < KNN_CWARPS; ++w) {
+                    cbox[c] = fminf(cbox[c], ctl->wbox[w][c]);
+                    cbox[3 + c] = fmaxf(cbox[3 + c], ctl->wbox[w][3 + c]);
+                }
+            }
+            int64_t centre = (int64_t)((double)(q_first + LS / 2) / (double)(A.n_query > 0 ? A.n_query : 1) *
+                                       (double)total_tiles);
+            if (centre < tile_lo) centre = tile_lo;
+            if (centre >= tile_hi) centre = tile_hi - 1;
+            int64_t up = centre, down = centre - 1;
+            while (up < tile_hi || down >= tile_lo) {
+                const int64_t t = lane < 16 ? up + lane : down - (lane - 16);
+                const bool in = lane < 16 ? t < tile_hi : t >= tile_lo;
+                const float d2 = in ? box_dist2(cbox, A.boxes + t * 6) : CUDART_INF_F;
+                up += 16;
+                down -= 16;
+                float worst = 0.f;
+                for (int w = 0; w < KNN_CWARPS; ++w) worst = fmaxf(worst, ctl->wtau[w]);
+                const unsigned cand = __ballot_sync(0xffffffffu, in && !(d2 > worst * (1.f + 1e-4f) + 1e-12f));
+                for (int r = 0; r < 32; ++r) {  // nearest first: up[0], down[0], up[1], ...
+                    const int l = (r >> 1) + ((r & 1) << 4);
+                    if (!((cand >> l) & 1u)) continue;
+                    const int tt = __shfl_sync(0xffffffffu, (int)t, l);
+                    const float dd = __shfl_sync(0xffffffffu, d2, l);
+                    int go = 0;
+                    if (lane == 0) {
+                        float now = 0.f;
+                        for (int w = 0; w < KNN_CWARPS; ++w) now = fmaxf(now, ctl->wtau[w]);
+                        go = !(dd > now * (1.f + 1e-4f) + 1e-12f);
+                    }
+                    go = __shfl_sync(0xffffffffu, go, 0);
+                    if (go) push(tt);
+                }
+            }
+        }
+        push(-1);
+        if (A.stats && lane == 0) {
+            atomicAdd(A.stats + 3, loaded);
+            atomicMax(A.stats + 4, loaded);
         }
         return;
     }
 
     // ================= consumer warps =================
     const int warp = tid >> 5;
-    int qcnt = 0;
-    uint32_t* myq = queue + tid;
+    int qcnt[Q];
+#pragma unroll
+    for (int qq = 0; qq < Q; ++qq) qcnt[qq] = 0;
+    unsigned char* myq = queue + tid;
+    const float* tile_x = nullptr;   // exact rows of the tile being scanned
+    int64_t tile_r0 = 0;
 
-    // Drain: every lane evaluates its queued (query, row) pairs exactly and inserts.
-    // Candidate order is (value, original id), so the result does not depend on visit order.
+    // Drain, per query slot: (1) the warp's queued (query, row) pairs are dealt out evenly over
+    // the 32 lanes, whichever lane queued them -- exact fp32 metric of the owner's query row
+    // (shared-memory column) against the tile's exact row (shared memory), value parked next
+    // to the queue entry; (2) every lane walks its own values and inserts the few that beat
+    // its k-th best.  Candidate order is (value, original id): the result does not depend on
+    // visit order.
     auto drain = [&]() {
-        int maxc = qcnt;
+        const int lane = tid & 31;
+        const int wbase = warp * 32;
+        int* pre = ctl->pre[warp];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-        for (int e = 0; e < maxc; ++e) {
-            if (e < qcnt) {
-                const uint32_t ent = myq[e * KNN_CTHREADS];
-                const int qq = (int)(ent >> 28);
-                const long long pos = (long long)(ent & 0x0fffffffu);
-                const int col = qq * KNN_CTHREADS + tid;
-                if (pos < ref_end) {
-                    const long long id = A.perm ? (long long)__ldg(A.perm + pos) : pos;
-                    const long long qrow = A.qperm ? (long long)__ldg(A.qperm + q_first + col) : q_first + col;
-                    const long long qid = A.query_id0 + qrow;
-                    bool ok = true;
-                    if ((A.flags & 1) && id == qid) ok = false;
-                    if ((A.flags & 2) && id >= qid) ok = false;
-                    if (ok) {
-                        const float v = exact_metric(A.M, A.xquery + qrow * A.ldx, A.xref + id * A.ldx);
-                        float* lvc = lv + col;
-                        int* lic = li + col;
-                        const float tv = lvc[(kc - 1) * LS];
-                        if (v < tv || (v == tv && (int)id < lic[(kc - 1) * LS])) {
-                            int p = kc - 1;
-                            while (p > 0) {
-                                const float u = lvc[(p - 1) * LS];
-                                const int ui = lic[(p - 1) * LS];
-                                if (!(u > v || (u == v && ui > (int)id))) break;
-                                lvc[p * LS] = u;
-                                lic[p * LS] = ui;
-                                --p;
-                            }
-                            lvc[p * LS] = v;
-                            lic[p * LS] = (int)id;
-                            const float tau = lvc[(kc - 1) * LS];
-                            if (tau < CUDART_INF_F) {
-                                const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
+        for (int qq = 0; qq < Q; ++qq) {
+            const int cnt = qcnt[qq];
+            int incl = cnt;
 #pragma unroll
-                                for (int k2 = 0; k2 < Q; ++k2)
-                                    if (k2 == qq) {
-                                        thr[k2] = tf - Aq[k2];
-                                        tauf[k2] = tf;
-                                    }
-                            }
-                            if (A.stats) atomicAdd(A.stats + 1, 1ull);
-                        }
-                        if (A.stats) atomicAdd(A.stats, 1ull);
-                    }
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
             }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            if (lane == 0) pre[0] = 0;
+            pre[lane + 1] = incl;
+            __syncwarp();
+            for (int g0 = 0; g0 < total; g0 += 32 * KNN_DU) {  // KNN_DU independent pairs per lane in flight
+                float vv[KNN_DU];
+                int att[KNN_DU];
+#pragma unroll
+                for (int u = 0; u < KNN_DU; ++u) {
+                    const int g = g0 + 32 * u + lane;
+                    const int gc = g < total ? g : 0;
+                    int o = 0;  // owner lane: the largest o with pre[o] <= gc
+#pragma unroll
+                    for (int b = 16; b > 0; b >>= 1)
+                        if (pre[o + b] <= gc) o += b;
+                    const int e = gc - pre[o];
+                    const int ocol = qq * KNN_CTHREADS + wbase + o;
+                    const int at = (qq * KNN_QC + e) * KNN_CTHREADS + wbase + o;
+                    const int j = queue[at];
+                    const int64_t pos = tile_r0 + j;
+                    bool ok = pos < ref_end;
+                    if ((A.flags & 5) == 5) ok = ok && pos != q_first + ocol;  // same scan order: self = same position
+                    if (A.flags & 2) ok = ok && pos < A.query_id0 + q_first + ocol;  // causal searches keep row order
+                    const float v = exact_metric(A.M, xq + ocol, LS, tile_x + (size_t)j * S);
+                    vv[u] = ok ? v : CUDART_INF_F;
+                    att[u] = g < total ? at : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < KNN_DU; ++u)
+                    if (att[u] >= 0) qval[att[u]] = vv[u];
+            }
+            if (A.stats && lane == 0) atomicAdd(A.stats, (unsigned long long)total);
+            __syncwarp();
+            const int col = qq * KNN_CTHREADS + tid;
+            float* lvc = lv + col;
+            int* lic = li + col;
+            for (int e = 0; e < cnt; ++e) {
+                const int at = (qq * KNN_QC + e) * KNN_CTHREADS + tid;
+                const float v = qval[at];
+                const float tv = lvc[(kc - 1) * LS];
+                if (!(v <= tv) || !(v < CUDART_INF_F)) continue;
+                const int64_t pos = tile_r0 + queue[at];
+                const int64_t id = A.perm ? (int64_t)__ldg(A.perm + pos) : pos;
+                if ((A.flags & 5) == 1 && id == A.query_id0 + qrow[qq]) continue;  // self, found by id
+                if (v == tv && (int)id >= lic[(kc - 1) * LS]) continue;
+                int p = kc - 1;
+                while (p > 0) {
+                    const float u = lvc[(p - 1) * LS];
+                    const int ui = lic[(p - 1) * LS];
+                    if (!(u > v || (u == v && ui > (int)id))) break;
+                    lvc[p * LS] = u;
+                    lic[p * LS] = ui;
+                    --p;
+                }
+                lvc[p * LS] = v;
+                lic[p * LS] = (int)id;
+                const float tau = lvc[(kc - 1) * LS];
+                if (tau < CUDART_INF_F) {
+                    const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
+                    thr[qq] = tf - Aq[qq];
+                    tauf[qq] = tf;
+                }
+                if (A.stats) atomicAdd(A.stats + 1, 1ull);
+            }
+            qcnt[qq] = 0;
+            __syncwarp();
         }
-        qcnt = 0;
         // publish the warp's worst bound for the producer's culling test
         float worst = 0.f;
 #pragma unroll
@@ -489,9 +601,10 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             skip = d2 > ctl->wtau[warp] * (1.f + 1e-4f) + 1e-12f;
         }
         if (!skip) {
-            const uint32_t tile_s = tiles_s + (uint32_t)s * KNN_TILE * W * 4;
+            const uint32_t tile_s = ring_s + (uint32_t)(s * stage_floats * sizeof(float));
+            tile_x = ring + s * stage_floats + KNN_TILE * W;
+            tile_r0 = r0;
             const int cnt4 = (cnt + KNN_RU - 1) & ~(KNN_RU - 1);  // stale rows of a partial tile are rejected by position
-            const uint32_t id0 = (uint32_t)r0;
             // software pipeline: the rows of step j+1 are loaded while step j is evaluated
             float4 rn[KNN_RU][F4];
 #pragma unroll
@@ -526,29 +639,36 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                         }
                         sv[qq][u] = acc;
                     }
-                    const float m = fminf(fminf(sv[qq][0], sv[qq][1]), fminf(sv[qq][2], sv[qq][3]));
+                    float m = sv[qq][0];
+#pragma unroll
+                    for (int u = 1; u < KNN_RU; ++u) m = fminf(m, sv[qq][u]);
                     worst = fminf(worst, m - thr[qq]);
                 }
-                // one warp-uniform branch per step; everything below it is rare
+                // one warp-uniform branch per step
                 if (__any_sync(0xffffffffu, worst <= 0.f)) {
+                    int fill = 0;
 #pragma unroll
-                    for (int qq = 0; qq < Q; ++qq)
+                    for (int qq = 0; qq < Q; ++qq) {
 #pragma unroll
                         for (int u = 0; u < KNN_RU; ++u)
                             if (sv[qq][u] <= thr[qq]) {
-                                myq[qcnt * KNN_CTHREADS] = ((uint32_t)qq << 28) | (id0 + (uint32_t)(j + u));
-                                ++qcnt;
+                                myq[(qq * KNN_QC + qcnt[qq]) * KNN_CTHREADS] = (unsigned char)(j + u);
+                                ++qcnt[qq];
                             }
-                    if (__any_sync(0xffffffffu, qcnt > KNN_QSLACK)) drain();
+                        fill = max(fill, qcnt[qq]);
+                    }
+                    if (__any_sync(0xffffffffu, fill > KNN_QSLACK)) drain();
                 }
             }
-            // tighten before the next culling decision
-            if (cull && __any_sync(0xffffffffu, qcnt > 0)) drain();
+            // the tile's exact rows leave with the tile: drain before releasing the slot
+            int pending = 0;
+#pragma unroll
+            for (int qq = 0; qq < Q; ++qq) pending |= qcnt[qq];
+            if (__any_sync(0xffffffffu, pending != 0)) drain();
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty_s + 8 * s);
     }
-    drain();
 
     // ---- write the candidate columns (rows in ORIGINAL query order) ----------------
 #pragma unroll
@@ -556,8 +676,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
         const int64_t qi = q_first + qq * KNN_CTHREADS + tid;
         if (qi >= A.n_query) continue;
         const int col = qq * KNN_CTHREADS + tid;
-        const int64_t qrow = A.qperm ? (int64_t)A.qperm[qi] : qi;
-        const size_t o = ((size_t)qrow * A.n_splits + blockIdx.y) * kc;
+        const size_t o = ((size_t)qrow[qq] * A.n_splits + blockIdx.y) * kc;
         for (int c = 0; c < kc; ++c) {
             const int id = li[c * LS + col];
             A.out_idx[o + c] = id == 0x7fffffff ? -1 : id;
@@ -620,15 +739,16 @@ int fill_metric(const mmmp_metric* m, int ldx, MetricDev& M) {
     return MMMP_OK;
 }
 
-size_t scan_smem(int F4, int Q, int kc) {
+size_t scan_smem(int F4, int Q, int kc, int S) {
     const size_t w = F4 * 4, ls = (size_t)KNN_CTHREADS * Q;
-    return (size_t)KNN_STAGES * KNN_TILE * w * 4 + (size_t)kc * ls * 8 + (size_t)knn_qcap(Q) * KNN_CTHREADS * 4 +
-           2 * KNN_STAGES * 8 + sizeof(ScanCtl) + 16;
+    size_t b = (size_t)KNN_STAGES * knn_stage_floats((int)w, S) * 4 + (size_t)kc * ls * 8 + (size_t)S * ls * 4;
+    b = knn_align(b + (size_t)Q * KNN_QC * KNN_CTHREADS * 5, 8);
+    return b + 2 * KNN_STAGES * 8 + sizeof(ScanCtl) + 16;
 }
 
 template <int F4, int Q>
 int launch_scan(const KnnArgs& A, int n_qblocks, void* stream) {
-    const size_t smem = scan_smem(F4, Q, A.kc);
+    const size_t smem = scan_smem(F4, Q, A.kc, A.S);
     MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_qblocks, A.n_splits, 1);
     MMMP_LAUNCH((knn_scan_kernel<F4, Q>), grid, KNN_THREADS, smem, stream, A);
@@ -670,15 +790,16 @@ int spatial_perm(const float* rows, int ld, int nd, int64_t n, const int* bbox_d
 
 }  // namespace
 
-extern "C" int mmmp_knn_stats(int enable, unsigned long long* out4_h) {
+extern "C" int mmmp_knn_stats(int enable, unsigned long long* out5_h) {
+    constexpr size_t bytes = 5 * sizeof(unsigned long long);
     if (enable && !g_knn_stats) {
-        MMMP_CUDA_TRY(cudaMalloc(&g_knn_stats, 4 * sizeof(unsigned long long)));
-        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, 4 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMalloc(&g_knn_stats, bytes));
+        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, bytes));
     }
-    if (out4_h && g_knn_stats) {
+    if (out5_h && g_knn_stats) {
         MMMP_CUDA_TRY(cudaDeviceSynchronize());
-        MMMP_CUDA_TRY(cudaMemcpy(out4_h, g_knn_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, 4 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMemcpy(out5_h, g_knn_stats, bytes, cudaMemcpyDeviceToHost));
+        MMMP_CUDA_TRY(cudaMemset(g_knn_stats, 0, bytes));
     }
     if (!enable && g_knn_stats) {
         cudaFree(g_knn_stats);
@@ -701,6 +822,7 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     const int W = width_for(fdim);
     if (!W) return MMMP_ERR_LIMIT;
     const int F4 = W / 4;
+    const int S = A.M.dim | 1;  // odd row stride: exact rows of a tile fall into distinct banks
     if (n_query == 0) return MMMP_OK;
     mmmp_pool_keep();
     cudaStream_t s = (cudaStream_t)stream;
@@ -708,16 +830,16 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     MMMP_CUDA_TRY(cudaGetDevice(&dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // queries per thread (measured on B200: Q = 2 beats 4 and 8 -- more resident warps win)
-    const int qmax = F4 <= 1 ? 8 : (F4 <= 2 ? 4 : (F4 <= 4 ? 2 : 1));
+    // queries per thread: measured on B200 (1M x 1M, FK and joint-space metrics), one query per
+    // thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM
+    const int qmax = F4 <= 2 ? 2 : 1;
     int Q = 1;
-    if (qmax >= 2 && n_query >= (int64_t)sms * KNN_CTHREADS * 2 * 2) Q = 2;
     if (const char* e = getenv("MMMP_KNN_Q")) {
         const int q = atoi(e);
-        if ((q == 1 || q == 2 || q == 4 || q == 8) && q <= qmax) Q = q;
+        if ((q == 1 || q == 2) && q <= qmax) Q = q;
     }
-    while (Q > 1 && scan_smem(F4, Q, k) > (size_t)max_smem) Q >>= 1;
-    if (scan_smem(F4, Q, k) > (size_t)max_smem) return MMMP_ERR_LIMIT;
+    while (Q > 1 && scan_smem(F4, Q, k, S) > (size_t)max_smem) Q >>= 1;
+    if (scan_smem(F4, Q, k, S) > (size_t)max_smem) return MMMP_ERR_LIMIT;
     bool cull = !causal && n_ref >= KNN_CULL_MIN;
     if (const char* e = getenv("MMMP_KNN_CULL")) cull = cull && atoi(e) != 0;
     const int n_qblocks = mmmp_div_up(n_query, (int64_t)KNN_CTHREADS * Q);
@@ -728,16 +850,17 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         if (n_splits > 32) n_splits = 32;
         if (n_splits > total_tiles) n_splits = (int)(total_tiles > 0 ? total_tiles : 1);
     }
-    const bool same = (fquery == fref && n_query == n_ref);
+    const bool same = (fquery == fref && xquery == xref && n_query == n_ref);
     // temporaries (library-owned, stream ordered)
-    float *pref = nullptr, *pquery = nullptr, *boxes = nullptr;
+    float *pref = nullptr, *pquery = nullptr, *boxes = nullptr, *xs = nullptr;
     int32_t *perm = nullptr, *qperm = nullptr, *tmp_idx = nullptr;
     int* bbox = nullptr;
     float* tmp_val = nullptr;
     const int nd = fdim < 3 ? fdim : 3;
     const size_t n_out = (size_t)n_query * n_splits * k;
+    const int64_t n_ref4 = (n_ref + 3) & ~(int64_t)3;
     auto cleanup = [&]() {
-        void* ptrs[] = {pref, same ? nullptr : pquery, boxes, perm, same ? nullptr : qperm, bbox, tmp_idx, tmp_val};
+        void* ptrs[] = {pref, same ? nullptr : pquery, boxes, xs, perm, same ? nullptr : qperm, bbox, tmp_idx, tmp_val};
         for (void* p : ptrs)
             if (p) cudaFreeAsync(p, s);
     };
@@ -750,6 +873,7 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         }                                                   \
     } while (0)
     KNN_TRY(cudaMallocAsync(&pref, (size_t)(n_ref > 0 ? n_ref : 1) * W * sizeof(float), s));
+    KNN_TRY(cudaMallocAsync(&xs, (size_t)(n_ref4 > 0 ? n_ref4 : 4) * S * sizeof(float), s));
     if (!same) KNN_TRY(cudaMallocAsync(&pquery, (size_t)n_query * W * sizeof(float), s));
     KNN_TRY(cudaMallocAsync(&tmp_idx, n_out * sizeof(int32_t), s));
     KNN_TRY(cudaMallocAsync(&tmp_val, n_out * sizeof(float), s));
@@ -773,7 +897,11 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         }
         KNN_TRY(cudaMallocAsync(&boxes, sizeof(float) * 6 * (total_tiles > 0 ? total_tiles : 1), s));
     }
-    if (n_ref > 0) MMMP_LAUNCH(knn_pack_kernel, grid_for(n_ref, sms), 256, 0, stream, fref, ldf, fdim, n_ref, perm, pref, W);
+    if (n_ref > 0) {
+        MMMP_LAUNCH(knn_pack_kernel, grid_for(n_ref, sms), 256, 0, stream, fref, ldf, fdim, n_ref, perm, pref, W);
+        MMMP_LAUNCH(knn_pack_exact_kernel, grid_for(n_ref4 * S, sms), 256, 0, stream, xref, ldx, A.M.dim, n_ref, n_ref4,
+                    perm, xs, S);
+    }
     if (same) {
         pquery = pref;
         qperm = perm;
@@ -781,10 +909,10 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         MMMP_LAUNCH(knn_pack_kernel, grid_for(n_query, sms), 256, 0, stream, fquery, ldf, fdim, n_query, qperm, pquery, W);
     }
     if (cull && total_tiles > 0)
-        MMMP_LAUNCH(tile_box_kernel, (int)total_tiles, 256, 0, stream, pref, W, nd, n_ref, boxes);
+        MMMP_LAUNCH(tile_box_kernel, (int)total_tiles, KNN_TILE, 0, stream, pref, W, nd, n_ref, boxes);
     A.pref = pref;
     A.pquery = pquery;
-    A.xref = xref;
+    A.xs = xs;
     A.xquery = xquery;
     A.perm = perm;
     A.qperm = qperm;
@@ -793,8 +921,9 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     A.n_query = n_query;
     A.query_id0 = query_id0;
     A.ldx = ldx;
+    A.S = S;
     A.kc = k;
-    A.flags = (exclude_self ? 1 : 0) | (causal ? 2 : 0);
+    A.flags = (exclude_self ? 1 : 0) | (causal ? 2 : 0) | ((same && query_id0 == 0) ? 4 : 0);
     A.n_splits = n_splits;
     A.tiles_per_split = (int)((total_tiles + n_splits - 1) / n_splits);
     if (A.tiles_per_split < 1) A.tiles_per_split = 1;
@@ -804,13 +933,9 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     switch (F4 * 10 + Q) {
         case 11: rc = launch_scan<1, 1>(A, n_qblocks, stream); break;
         case 12: rc = launch_scan<1, 2>(A, n_qblocks, stream); break;
-        case 14: rc = launch_scan<1, 4>(A, n_qblocks, stream); break;
-        case 18: rc = launch_scan<1, 8>(A, n_qblocks, stream); break;
         case 21: rc = launch_scan<2, 1>(A, n_qblocks, stream); break;
         case 22: rc = launch_scan<2, 2>(A, n_qblocks, stream); break;
-        case 24: rc = launch_scan<2, 4>(A, n_qblocks, stream); break;
         case 41: rc = launch_scan<4, 1>(A, n_qblocks, stream); break;
-        case 42: rc = launch_scan<4, 2>(A, n_qblocks, stream); break;
         case 81: rc = launch_scan<8, 1>(A, n_qblocks, stream); break;
         default: rc = MMMP_ERR_LIMIT;
     }

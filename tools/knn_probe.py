@@ -21,7 +21,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 q64, q32 = core.sample_uniform(lim[:, 0], lim[:, 1], n, 7)
 L = _lib.load()
 for name, F in (("fk", w.fk_features(q64, q32, 0)), ("l2", core.l2_features(q64, q32))):
-    for Q in (1, 2, 4, 8):
+    for Q in (1, 2):
         os.environ["MMMP_KNN_Q"] = str(Q)
         L.mmmp_knn_stats(1, None)
         for it in range(2):
@@ -31,10 +31,10 @@ for name, F in (("fk", w.fk_features(q64, q32, 0)), ("l2", core.l2_features(q64,
             ci, cd = core.knn(F, F, 16)
             e1.record()
             torch.cuda.synchronize()
-        st = (C.c_ulonglong * 4)()
+        st = (C.c_ulonglong * 5)()
         L.mmmp_knn_stats(1, st)
         ms = e0.elapsed_time(e1)
         print(f"{name} n={n} Q={Q}: {ms:.1f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  exact/query={st[0] / 2 / n:.0f} "
               f"ins/query={st[1] / 2 / n:.0f} drains/warp={st[2] / 2 / (n / 32 / Q):.0f} "
-              f"tiles loaded/CTA={st[3] / 2 / max(n / 128 / Q, 1):.0f} of {(n + 255) // 256}", flush=True)
+              f"tiles loaded/CTA={st[3] / 2 / max(n / 128 / Q, 1):.0f} (max {st[4]}) of {(n + 127) // 128}", flush=True)
         L.mmmp_knn_stats(0, None)
