@@ -202,7 +202,8 @@ int mmmp_collide_configs(const mmmp_world* w, int robot, const void* q_d, int ld
  * n_steps <= 64 evaluate a step only when no earlier evaluation of the same
  * edge proves it free: an evaluation returns the clearance of the sphere
  * model, and |d centre / d q_m| <= lever arm bounds how far every sphere can
- * move per step, so the verdict equals the OR over all steps.               */
+ * move per step, so the verdict equals the OR over all steps.  Edges on
+ * which that proves little are finished by a warp-per-edge pass.            */
 int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
                        const int32_t* edges_d, int64_t E, int n_steps, double step,
                        uint32_t flags, uint8_t* out_d, void* stream);
@@ -211,10 +212,11 @@ int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
 int mmmp_collide_segments(const mmmp_world* w, int robot, const void* qa_d, const void* qb_d,
                           int ld, int64_t E, int n_steps, double step,
                           uint32_t flags, uint8_t* out_d, void* stream);
-/* profiling aid: enable != 0 turns on two device counters of the spatial edge
- * kernels (edges decided, configurations evaluated); out2_h (may be NULL)
- * receives and resets them; enable == 0 frees them.                         */
-int mmmp_edge_stats(int enable, unsigned long long* out2_h);
+/* profiling aid: enable != 0 turns on four device counters of the spatial edge
+ * kernels (edges seen, configurations evaluated by the step-skipping pass,
+ * edges deferred to the warp-per-edge pass, configurations evaluated there);
+ * out4_h (may be NULL) receives and resets them; enable == 0 frees them.    */
+int mmmp_edge_stats(int enable, unsigned long long* out4_h);
 /* robot_robot_collision(q1, q2, r1, r2) on a pair list
  * (decoupled_prm.py:871-876; cbsprm.py:165-183): qa_d rows are robot ra's
  * joints, qb_d rows robot rb's.                                            */

@@ -476,8 +476,9 @@ template <int L>
 __global__ void __launch_bounds__(128, 4)
 collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base,
                               int ld, const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
-                              float want_scale, unsigned long long* __restrict__ stats,
-                              uint8_t* __restrict__ out) {
+                              float want_scale, int hard_after, int64_t* __restrict__ hard_edge,
+                              unsigned long long* __restrict__ hard_mask, unsigned long long* __restrict__ hard_count,
+                              unsigned long long* __restrict__ stats, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     SpatialSmem* hdr;
     RobotDev* robs;
@@ -504,13 +505,14 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
 
     int64_t e = -1;
     uint64_t mask = 0;
-    bool collided = false;
+    bool collided = false, deferred = false;
+    int rounds = 0;
     const float *pa = qa_base, *pb = qa_base;
     unsigned n_evals = 0;
     while (true) {
         // ---- groups without undecided steps: write the verdict, take the next edge
         const bool need = mask == 0;
-        if (need && e >= 0 && gl == 0) out[e] = collided ? 1 : 0;
+        if (need && e >= 0 && gl == 0 && !deferred) out[e] = collided ? 1 : 0;
         const unsigned needb = __ballot_sync(FULL, need && gl == 0);
         bool table_hit = false;
         if (need) {
@@ -519,6 +521,8 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
             if (cand < w_end) {
                 e = cand;
                 collided = false;
+                deferred = false;
+                rounds = 0;
                 mask = all_steps;
                 if (edges) {
                     const int ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
@@ -580,6 +584,26 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
         } else {
             mask &= ~cover;
         }
+        ++rounds;
+        // An edge on which the first rounds prove little (clearance below the travel per step) will
+        // have nearly every step evaluated: hand it, with its undecided steps, to the warp-per-edge
+        // pass that follows (coherent lanes, verdict-only evaluation).
+        const bool defer = hard_edge && mask != 0 && rounds <= 2 && __popcll(mask) > hard_after;
+        const unsigned db = __ballot_sync(FULL, defer && gl == 0);
+        if (db) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(hard_count, (unsigned long long)__popc(db));
+            base = __shfl_sync(FULL, base, 0);
+            if (defer) {
+                if (gl == 0) {
+                    const unsigned long long at = base + __popc(db & leaders_below);
+                    hard_edge[at] = e;
+                    hard_mask[at] = mask;
+                }
+                deferred = true;
+                mask = 0;
+            }
+        }
     }
     if (stats) {
 #pragma unroll
@@ -589,6 +613,61 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
             const int64_t first = warp_id * chunk;
             if (w_end > first) atomicAdd(stats, (unsigned long long)(w_end - first));
         }
+    }
+}
+
+// Second pass over the edges the kernel above deferred: one warp per edge, the lanes take the
+// undecided steps (bit mask) in order, verdict-only evaluation, warp-ballot early exit.  The
+// pair tables were already looked up for every step of a deferred edge.
+__global__ void __launch_bounds__(128, 4)
+collide_edges_hard_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base, int ld,
+                          const int32_t* __restrict__ edges, const int64_t* __restrict__ hard_edge,
+                          const unsigned long long* __restrict__ hard_mask,
+                          const unsigned long long* __restrict__ hard_count, double step,
+                          unsigned long long* __restrict__ stats, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SpatialSmem* hdr;
+    RobotDev* robs;
+    ObstacleDev* obs;
+    float* frames;
+    stage_world(A, smem, hdr, robs, obs, frames);
+    float* cs = frames + threadIdx.x;
+    const int stride = blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int64_t n_hard = (int64_t)*hard_count;
+    unsigned n_evals = 0;
+    for (int64_t h = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); h < n_hard;
+         h += (int64_t)gridDim.x * warps_per_cta) {
+        const int64_t e = hard_edge[h];
+        const uint64_t mask = hard_mask[h];
+        const float *pa, *pb;
+        if (edges) {
+            pa = qa_base + (int64_t)__ldg(edges + 2 * e) * ld;
+            pb = qa_base + (int64_t)__ldg(edges + 2 * e + 1) * ld;
+        } else {
+            pa = qa_base + e * ld;
+            pb = qb_base + e * ld;
+        }
+        const int cnt = __popcll(mask);
+        bool any = false;
+        for (int r = lane; r < ((cnt + 31) & ~31) && !any; r += 32) {
+            bool hit = false;
+            if (r < cnt) {
+                ++n_evals;
+                const int i = nth_set_bit(mask, r);
+                QEdge ql{pa, pb, (float)((double)i * step)};
+                hit = spatial_eval<QEdge, false>(A.W, hdr, robs, obs, A.flags, cs, stride, ql, true, 0.f) < 0.f;
+            }
+            any = __any_sync(0xffffffffu, hit);
+        }
+        if (lane == 0) out[e] = any ? 1 : 0;
+    }
+    if (stats) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) n_evals += __shfl_xor_sync(0xffffffffu, n_evals, off);
+        if (lane == 0) atomicAdd(stats + 3, (unsigned long long)n_evals);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + 2, (unsigned long long)n_hard);
     }
 }
 
@@ -656,15 +735,16 @@ unsigned long long* g_edge_stats = nullptr;  // device counters, enabled by mmmp
 
 }  // namespace
 
-extern "C" int mmmp_edge_stats(int enable, unsigned long long* out2_h) {
+extern "C" int mmmp_edge_stats(int enable, unsigned long long* out4_h) {
+    constexpr size_t bytes = 4 * sizeof(unsigned long long);
     if (enable && !g_edge_stats) {
-        MMMP_CUDA_TRY(cudaMalloc(&g_edge_stats, 2 * sizeof(unsigned long long)));
-        MMMP_CUDA_TRY(cudaMemset(g_edge_stats, 0, 2 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMalloc(&g_edge_stats, bytes));
+        MMMP_CUDA_TRY(cudaMemset(g_edge_stats, 0, bytes));
     }
-    if (out2_h && g_edge_stats) {
+    if (out4_h && g_edge_stats) {
         MMMP_CUDA_TRY(cudaDeviceSynchronize());
-        MMMP_CUDA_TRY(cudaMemcpy(out2_h, g_edge_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        MMMP_CUDA_TRY(cudaMemset(g_edge_stats, 0, 2 * sizeof(unsigned long long)));
+        MMMP_CUDA_TRY(cudaMemcpy(out4_h, g_edge_stats, bytes, cudaMemcpyDeviceToHost));
+        MMMP_CUDA_TRY(cudaMemset(g_edge_stats, 0, bytes));
     }
     if (!enable && g_edge_stats) {
         cudaFree(g_edge_stats);
@@ -749,8 +829,36 @@ static int launch_edges(const mmmp_world* w, int robot, const float* qa, const f
         double refine = 0.0;
         if (const char* s = getenv("MMMP_EDGE_REFINE")) refine = atof(s);
         const float want_scale = (float)(step / 0.999 * refine);
+        // edges still holding more than hard_after undecided steps after their first two rounds go
+        // to the warp-per-edge pass (negative: never)
+        int hard_after = (n_steps * 3) / 5;
+        if (const char* s = getenv("MMMP_EDGE_HARD")) hard_after = atoi(s);
+        cudaStream_t st = (cudaStream_t)stream;
+        int64_t* hard_edge = nullptr;
+        unsigned long long *hard_mask = nullptr, *hard_count = nullptr;
+        int block2 = 0, grid2 = 0;
+        size_t smem2 = 0;
+        if (hard_after >= 0 && pick_launch(collide_edges_hard_kernel, w, A, 4, E, block2, smem2, grid2) != MMMP_OK)
+            hard_after = -1;
+        if (hard_after >= 0) {
+            mmmp_pool_keep();
+            MMMP_CUDA_TRY(cudaMallocAsync(&hard_edge, sizeof(int64_t) * E, st));
+            cudaError_t e1 = cudaMallocAsync(&hard_mask, sizeof(unsigned long long) * (E + 1), st);
+            if (e1 != cudaSuccess) {
+                cudaFreeAsync(hard_edge, st);
+                return MMMP_ERR_CUDA_BASE + (int)e1;
+            }
+            hard_count = hard_mask + E;
+            cudaMemsetAsync(hard_count, 0, sizeof(unsigned long long), st);
+        }
         MMMP_LAUNCH(collide_edges_adaptive_kernel<L>, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps,
-                    step, want_scale, g_edge_stats, out);
+                    step, want_scale, hard_after, hard_edge, hard_mask, hard_count, g_edge_stats, out);
+        if (hard_edge) {
+            MMMP_LAUNCH(collide_edges_hard_kernel, grid2, block2, smem2, stream, A, qa, qb, ld, edges, hard_edge,
+                        hard_mask, hard_count, step, g_edge_stats, out);
+            cudaFreeAsync(hard_edge, st);
+            cudaFreeAsync(hard_mask, st);
+        }
     }
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;

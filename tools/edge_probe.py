@@ -18,7 +18,8 @@ from mmmp_b200 import _lib, core  # noqa: E402
 from mmmp_b200._lib import CHECK_EXHAUSTIVE, CHECK_OBSTACLES, CHECK_SELF  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-refines = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1.0]
+refines = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.0]
+hards = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [30]
 L = _lib.load()
 model = core.load_model("panda_spheres")
 bases, obstacles = bench.scene(4)
@@ -52,12 +53,14 @@ def timed(flags, reps=3):
 ref, ms = timed(F | CHECK_EXHAUSTIVE)
 print(f"n={free32.shape[0]} E={E} exhaustive: {ms:.1f} ms  blocked {float(ref.float().mean()):.4f}", flush=True)
 for name, flags in (("self+obst", F), ("self", CHECK_SELF), ("obst", CHECK_OBSTACLES)):
-    for r in refines:
-        os.environ["MMMP_EDGE_REFINE"] = str(r)
+    for r in [(a, b) for a in refines for b in hards]:
+        os.environ["MMMP_EDGE_REFINE"] = str(r[0])
+        os.environ["MMMP_EDGE_HARD"] = str(r[1])
         L.mmmp_edge_stats(1, None)
         out, ms = timed(flags, reps=2)
-        st = (C.c_ulonglong * 2)()
+        st = (C.c_ulonglong * 4)()
         L.mmmp_edge_stats(1, st)
         L.mmmp_edge_stats(0, None)
         extra = f" mismatches {int((out != ref).sum())}" if flags == F else ""
-        print(f"{name:10s} refine={r:4.2f}: {ms:7.1f} ms  evaluations/edge {st[1] / max(st[0], 1):.2f}{extra}", flush=True)
+        print(f"{name:10s} refine={r[0]:4.2f} hard_after={r[1]:3d}: {ms:7.1f} ms  evaluations/edge {(st[1] + st[3]) / max(st[0], 1):.2f} "
+              f"(deferred {st[2] / max(st[0], 1):.3f} of the edges, {st[3] / max(st[0], 1):.2f} evaluations/edge there){extra}", flush=True)
