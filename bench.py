@@ -173,6 +173,32 @@ def workload_config(args):
             "l2": "per-step working set (>1 GB) exceeds the 126 MB L2 and a 256 MB buffer is rewritten between steps"}
 
 
+def kernel_counters(core, builder, args):
+    """Library counters of one arm's scan + edge check (untimed diagnostic launch)."""
+    import ctypes as C
+    from mmmp_b200 import _lib
+    try:
+        L = _lib.load()
+        q64, q32 = builder.sample_free(args.nodes, seed=4242)
+        L.mmmp_knn_stats(1, None)
+        L.mmmp_edge_stats(1, None)
+        res = builder.candidates(q64, q32, gather=False)
+        lo, hi = res["rows"]
+        ks, es = (C.c_ulonglong * 5)(), (C.c_ulonglong * 4)()
+        L.mmmp_knn_stats(1, ks)
+        L.mmmp_edge_stats(1, es)
+        L.mmmp_knn_stats(0, None)
+        L.mmmp_edge_stats(0, None)
+        nq = max(hi - lo, 1)
+        ctas = -(-nq // 128)
+        return {"tiles": int(ks[3]), "tiles_per_cta": ks[3] / ctas, "exact_per_query": ks[0] / nq,
+                "insert_per_query": ks[1] / nq, "evals_per_edge": (es[1] + es[3]) / max(es[0], 1),
+                "deferred_frac": es[2] / max(es[0], 1)}
+    except Exception as exc:  # diagnostics must never cost the bench line
+        sys.stderr.write(f"kernel_counters failed: {exc}\n")
+        return None
+
+
 # ------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -301,40 +327,61 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        # Dominant kernels: the neighbour scan and the edge-collision
-        # kernel take ~equal shares of a step.  `roofline` is the scan, reported against HBM as
-        # north_star asks, with the ALGORITHMIC streamed bytes of SURVEY.md 8d (exhaustive
-        # scan: ceil(Nq/Tq) * Nr * Dp * 4 + Nq * kc * 8; Tq = 256 queries per CTA, Dp = 4 packed
-        # filter columns, kc = k + 6 candidates); the kernel itself is L2/issue bound and skips
-        # the tiles its bounding-box test proves irrelevant, so `binding` carries the FP32 view.
+        # Two kernels share a step about equally: the neighbour scan and the
+        # edge-collision pair.  `roofline` is the scan, reported against HBM as north_star asks, with
+        # the ALGORITHMIC streamed bytes of SURVEY.md 8d for an exhaustive scan,
+        #     ceil(Nq / Tq) * Nr * Dp * 4 + Nq * kc * 8,
+        # Tq = 128 queries per CTA, Dp = 16 (15-D FK features padded), kc = k + 6 candidates.  The kernel
+        # skips every tile its bounding-box test proves irrelevant and its rows stay in the 126 MB L2,
+        # so the fraction can exceed 1: `executed` carries what one launch really moved and evaluated
+        # (library counters, read in an untimed launch after the timed region).
         n_launch = args.steps * args.arms
         scan_ms = phases.get("knn_scan", 0.0) / max(n_launch, 1)
         edge_ms = phases.get("edge_collision", 0.0) / max(n_launch, 1)
         nq = (args.nodes + world_size - 1) // world_size
-        TQ, DP, kc = 256, 4, args.k + 6
+        TQ, DP, kc = 128, 16, args.k + 6
         alg_bytes = -(-nq // TQ) * args.nodes * DP * 4 + nq * kc * 8
         pairs = nq * args.nodes
-        scan_flops = pairs * (2 * 3 + 1)              # 3 FFMA + 1 compare per pair (exhaustive count)
+        scan_flops = pairs * (5 * 9 + 5)             # FK-metric pair = 5 groups x 9 flop + 5
         sm_count, clock_mhz = 148, float(peaks.get("sm_max_mhz", 1965.0))
         fp32_peak = sm_count * 128 * 2 * clock_mhz * 1e6 / 1e12
-        # edge kernel: per configuration 504 flop of FK + sphere tests; only the FK
-        # part is a fixed algorithmic count, so the fraction below is a LOWER bound of pipe use
+        counters = kernel_counters(core, builders[0], args)
+        tile_bytes = 128 * (4 + 15) * 4              # filter row (4 floats) + exact row (15 floats) per reference
+        executed = None
+        if counters:
+            executed = {"tiles_loaded_per_cta": counters["tiles_per_cta"], "tiles_total_per_cta": -(-args.nodes // 128),
+                        "bytes_through_tma_per_launch": counters["tiles"] * tile_bytes,
+                        "exact_evaluations_per_query": counters["exact_per_query"],
+                        "insertions_per_query": counters["insert_per_query"]}
+        # edge pair: per configuration 504 flop of FK + 7 self link-pair and 10
+        # link-vs-plane bounding tests (8 and 4 flop) = 600 flop before any sphere-level descent;
+        # S = 50 steps per edge, S_eff = steps actually evaluated (library counter)
         edge_cfgs = nq * args.k * 50
-        edge_flops = edge_cfgs * 504
-        roof = {"bound": "hbm", "kernel": "knn_scan_kernel<1,2>", "achieved": alg_bytes / (scan_ms * 1e-3) / 1e9,
+        cfg_flop = 504 + 7 * 8 + 10 * 4
+        s_eff = counters["evals_per_edge"] if counters else None
+        roof = {"bound": "hbm", "kernel": "knn_scan_kernel<1,1>", "achieved": alg_bytes / (scan_ms * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (scan_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "ms_per_launch": scan_ms,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "binding": "L2 + FP32 issue: packed reference rows (16 MB per arm) stay in the 126 MB L2, the "
-                           "scan never touches HBM after the first pass",
+                "traffic": 418018816, "traffic_source": "ncu --set full, profiles/r01_knn_scan_full.csv "
+                                                        "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                "peak_source": peak_src, "ms_per_launch": scan_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "executed": executed,
+                "binding": "shared-memory/FP32 issue: the packed rows (76 MB per arm) stay in the 126 MB L2 and "
+                           "tile culling loads ~3 % of the tiles, so HBM is not the limiter; issue slots are "
+                           "(profiles/r01_knn_scan_full.csv: issue active, stall reasons)",
                 "fp32": {"achieved": scan_flops / (scan_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": scan_flops / (scan_ms * 1e-3) / 1e12 / fp32_peak,
-                         "note": "exhaustive-equivalent flops; tile culling executes a fraction of them",
+                         "note": "exhaustive-equivalent flops (SURVEY 8d); culling and the 3-flop centroid filter "
+                                 "execute a small fraction of them",
                          "peak_source": "148 SMs x 128 lanes x 2 x clocks.max.sm"},
-                "second_kernel": {"kernel": "collide_edges_kernel", "ms_per_launch": edge_ms,
-                                  "configs_per_s": edge_cfgs / (edge_ms * 1e-3) if edge_ms > 0 else None,
-                                  "fk_tflops": edge_flops / (edge_ms * 1e-3) / 1e12 if edge_ms > 0 else None,
-                                  "fp32_peak": fp32_peak, "bound": "FP32 pipe / issue"}}
+                "second_kernel": {"kernel": "collide_edges_adaptive_kernel<4> + collide_edges_hard_kernel",
+                                  "ms_per_launch_pair": edge_ms, "steps_per_edge": 50, "steps_evaluated_per_edge": s_eff,
+                                  "edges_deferred_to_warp_pass": counters["deferred_frac"] if counters else None,
+                                  "configs_per_s_nominal": edge_cfgs / (edge_ms * 1e-3) if edge_ms > 0 else None,
+                                  "configs_per_s_evaluated": (edge_cfgs * s_eff / 50) / (edge_ms * 1e-3)
+                                  if edge_ms > 0 and s_eff else None,
+                                  "tflops_evaluated_lower_bound": (edge_cfgs * s_eff / 50) * cfg_flop / (edge_ms * 1e-3) / 1e12
+                                  if edge_ms > 0 and s_eff else None,
+                                  "fp32_peak": fp32_peak, "bound": "FP32 pipe / issue (divergent sphere-level descents)"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",

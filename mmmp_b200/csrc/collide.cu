@@ -616,9 +616,12 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
     }
 }
 
-// Second pass over the edges the kernel above deferred: one warp per edge, the lanes take the
-// undecided steps (bit mask) in order, verdict-only evaluation, warp-ballot early exit.  The
-// pair tables were already looked up for every step of a deferred edge.
+// Second pass over the edges the kernel above deferred: a warp takes MMMP_HARD_BATCH edges at
+// a time and deals their undecided steps (bit masks) out to its lanes as one list, so a round
+// spans one or two edges (coherent lanes) and only the last round of a batch is partly idle.
+// Verdict-only evaluation; an edge found colliding drops its remaining steps.  The pair tables
+// were already looked up for every step of a deferred edge.
+#define MMMP_HARD_BATCH 8
 __global__ void __launch_bounds__(128, 4)
 collide_edges_hard_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base, int ld,
                           const int32_t* __restrict__ edges, const int64_t* __restrict__ hard_edge,
@@ -633,39 +636,60 @@ collide_edges_hard_kernel(SpatialArgs A, const float* __restrict__ qa_base, cons
     stage_world(A, smem, hdr, robs, obs, frames);
     float* cs = frames + threadIdx.x;
     const int stride = blockDim.x;
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
     const int64_t n_hard = (int64_t)*hard_count;
     unsigned n_evals = 0;
-    for (int64_t h = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); h < n_hard;
-         h += (int64_t)gridDim.x * warps_per_cta) {
-        const int64_t e = hard_edge[h];
-        const uint64_t mask = hard_mask[h];
-        const float *pa, *pb;
-        if (edges) {
-            pa = qa_base + (int64_t)__ldg(edges + 2 * e) * ld;
-            pb = qa_base + (int64_t)__ldg(edges + 2 * e + 1) * ld;
-        } else {
-            pa = qa_base + e * ld;
-            pb = qb_base + e * ld;
+    for (int64_t h0 = ((int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * MMMP_HARD_BATCH; h0 < n_hard;
+         h0 += (int64_t)gridDim.x * warps_per_cta * MMMP_HARD_BATCH) {
+        // lane b < BATCH holds edge h0 + b: id, mask, end points, running verdict
+        int64_t my_e = -1;
+        uint64_t my_mask = 0;
+        if (lane < MMMP_HARD_BATCH && h0 + lane < n_hard) {
+            my_e = hard_edge[h0 + lane];
+            my_mask = hard_mask[h0 + lane];
         }
-        const int cnt = __popcll(mask);
-        bool any = false;
-        for (int r = lane; r < ((cnt + 31) & ~31) && !any; r += 32) {
+        int incl = __popcll(my_mask);
+#pragma unroll
+        for (int o = 1; o < MMMP_HARD_BATCH; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const int total = __shfl_sync(FULL, incl, MMMP_HARD_BATCH - 1);
+        unsigned dead = 0;  // bit b: edge b of the batch already found colliding
+        for (int g0 = 0; g0 < total; g0 += 32) {
+            const int g = g0 + lane;
+            int b = 0;  // edge of the batch that owns list item g
+#pragma unroll
+            for (int bb = 0; bb < MMMP_HARD_BATCH - 1; ++bb) b += (g >= __shfl_sync(FULL, incl, bb)) ? 1 : 0;
+            const int before = __shfl_sync(FULL, incl, b) - __popcll(__shfl_sync(FULL, my_mask, b));
+            const int64_t e = __shfl_sync(FULL, my_e, b);
+            const uint64_t mask = __shfl_sync(FULL, my_mask, b);
             bool hit = false;
-            if (r < cnt) {
+            if (g < total && !((dead >> b) & 1u)) {
                 ++n_evals;
-                const int i = nth_set_bit(mask, r);
+                const int i = nth_set_bit(mask, g - before);
+                const float *pa, *pb;
+                if (edges) {
+                    pa = qa_base + (int64_t)__ldg(edges + 2 * e) * ld;
+                    pb = qa_base + (int64_t)__ldg(edges + 2 * e + 1) * ld;
+                } else {
+                    pa = qa_base + e * ld;
+                    pb = qb_base + e * ld;
+                }
                 QEdge ql{pa, pb, (float)((double)i * step)};
                 hit = spatial_eval<QEdge, false>(A.W, hdr, robs, obs, A.flags, cs, stride, ql, true, 0.f) < 0.f;
             }
-            any = __any_sync(0xffffffffu, hit);
+#pragma unroll
+            for (int bb = 0; bb < MMMP_HARD_BATCH; ++bb)
+                if (__any_sync(FULL, hit && b == bb)) dead |= 1u << bb;
         }
-        if (lane == 0) out[e] = any ? 1 : 0;
+        if (my_e >= 0) out[my_e] = (dead >> lane) & 1u;
     }
     if (stats) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) n_evals += __shfl_xor_sync(0xffffffffu, n_evals, off);
+        for (int off = 16; off > 0; off >>= 1) n_evals += __shfl_xor_sync(FULL, n_evals, off);
         if (lane == 0) atomicAdd(stats + 3, (unsigned long long)n_evals);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + 2, (unsigned long long)n_hard);
     }
