@@ -213,7 +213,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the roadmap path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))   # a lost rank fails fast
     if rank == 0:
         _build.build()
     if world_size > 1:
@@ -345,7 +347,10 @@ def run_ours(args):
         scan_flops = pairs * (5 * 9 + 5)             # FK-metric pair = 5 groups x 9 flop + 5
         sm_count, clock_mhz = 148, float(peaks.get("sm_max_mhz", 1965.0))
         fp32_peak = sm_count * 128 * 2 * clock_mhz * 1e6 / 1e12
-        counters = kernel_counters(core, builders[0], args)
+        # rank 0 alone, on a builder that does no collectives
+        counters = kernel_counters(core, RoadmapBuilder(world, 0, "fk", args.k, 50, 0.02, single_rank=True), args)
+        if counters and world_size > 1:
+            counters["tiles"] //= world_size      # a rank scans 1/world_size of the query blocks
         tile_bytes = 128 * (4 + 15) * 4              # filter row (4 floats) + exact row (15 floats) per reference
         executed = None
         if counters:
