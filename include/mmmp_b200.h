@@ -346,6 +346,17 @@ int mmmp_greedy_degree_connect(const int32_t* nbr_idx_h, const uint8_t* edge_fre
                                int64_t N, int k1, int k2, int cap, int32_t* adj_h,
                                int32_t* deg_h);
 
+/* Connected components of a roadmap: the partition computed by
+ * compute_connected_components (decoupled_prm.py:613-636).  adj_d [N, cap]
+ * int32 neighbour table, -1 padded (the accepted adjacency of
+ * mmmp_greedy_degree_connect, or a candidate table with mask_d [N, cap] = 1
+ * where the candidate edge is collision free; mask_d may be NULL); an edge may
+ * be listed from either end.  labels_d[i] = smallest node id of i's component
+ * (the node the reference's outer loop starts that component from);
+ * n_components_d (may be NULL) receives the number of components.          */
+int mmmp_connected_components(const int32_t* adj_d, const uint8_t* mask_d, int64_t N, int cap,
+                              int32_t* labels_d, int64_t* n_components_d, void* stream);
+
 /* library / device introspection */
 int mmmp_version(void);
 int mmmp_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);

@@ -123,6 +123,7 @@ SIGNATURES = {
     "mmmp_greedy_degree_connect": [_P, _P, _I64, _I, _I, _I, _P, _P],
     "mmmp_version": [],
     "mmmp_device_info": [_P, _P, _P, _P],
+    "mmmp_connected_components": [_P, _P, _I64, _I, _P, _P, _P],
     "mmmp_launch_count": [],
 }
 _RESTYPES = {"mmmp_launch_count": C.c_int64}

@@ -376,6 +376,24 @@ def greedy_degree_connect(nbr_idx: np.ndarray, edge_free: np.ndarray, k2: int, c
     return adj, deg
 
 
+def connected_components(adj: torch.Tensor, mask: Optional[torch.Tensor] = None):
+    """Partition of compute_connected_components (decoupled_prm.py:613-636) on the GPU.
+    adj [N, cap] int32 neighbour table (-1 padded), mask [N, cap] uint8 (1 = edge present) or None.
+    -> (labels [N] int32: smallest node id of the node's component, number of components)."""
+    dev = _require_cuda()
+    adj = _dev(adj, torch.int32)
+    n, cap = adj.shape
+    if mask is not None:
+        mask = _dev(mask, torch.uint8)
+        if tuple(mask.shape) != (n, cap):
+            raise MmmpError("connected_components: mask must have the shape of adj")
+    labels = torch.empty((n,), dtype=torch.int32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    _lib.call("mmmp_connected_components", _ptr(adj), _ptr(mask) if mask is not None else None, n, cap, _ptr(labels),
+              _ptr(count), _stream())
+    return labels, int(count.item())
+
+
 def launch_count() -> int:
     return int(_lib.load().mmmp_launch_count())
 

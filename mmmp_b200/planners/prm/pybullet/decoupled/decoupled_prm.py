@@ -327,12 +327,38 @@ class DecoupledPRM:
                     ed[nb.id].append(node.id)
 
     # ------------------------------------------------------------------ components (:613-704)
-    def compute_connected_components(self, r_id):
-        """Depth-first components in the reference's visiting order (stack, last in first out)."""
+    # roadmaps above this size get their components from the GPU union-find (same partition, the
+    # components in the reference's order, nodes inside a component by id instead of DFS order)
+    GPU_COMPONENTS_MIN_NODES = 50000
+
+    def component_labels(self, r_id):
+        """labels[i] = position (in the node list) of the first node of node i's component, on the
+        GPU (mmmp_connected_components); the partition of compute_connected_components (:613-636)."""
         r_index = self.r_ids.index(r_id)
-        by_id = {n.id: n for n in self.node_lists[r_index]}
+        nodes = self.node_lists[r_index]
+        pos = {n.id: i for i, n in enumerate(nodes)}
+        edges = self.edge_dicts[r_index]
+        cap = max(1, max((len(edges.get(n.id, ())) for n in nodes), default=1))
+        adj = np.full((len(nodes), cap), -1, dtype=np.int32)
+        for i, n in enumerate(nodes):
+            row = [pos[j] for j in edges.get(n.id, ()) if j in pos]
+            adj[i, :len(row)] = row
+        labels, _ = core.connected_components(torch.from_numpy(adj).to(core._require_cuda()))
+        return labels.cpu().numpy()
+
+    def compute_connected_components(self, r_id):
+        """Depth-first components in the reference's visiting order (stack, last in first out);
+        large roadmaps: the same components from the GPU labels, nodes in list order."""
+        r_index = self.r_ids.index(r_id)
+        nodes = self.node_lists[r_index]
+        if len(nodes) >= self.GPU_COMPONENTS_MIN_NODES:
+            labels = self.component_labels(r_id)
+            order = np.argsort(labels, kind="stable")            # by first node, then list order
+            cuts = np.nonzero(np.diff(labels[order]))[0] + 1
+            return [[nodes[i] for i in part] for part in np.split(order, cuts)]
+        by_id = {n.id: n for n in nodes}
         visited, components = set(), []
-        for node in self.node_lists[r_index]:
+        for node in nodes:
             if node.id in visited:
                 continue
             component, stack = [], [node]
@@ -349,6 +375,9 @@ class DecoupledPRM:
         return components
 
     def connect_connected_components_random(self, components, r_id, n_pairs=5, max_tries=20):
+        """:666-704.  The random tries of one component pair are drawn ahead (the draws do not depend
+        on the verdicts), checked in ONE batched launch, and the generator is then rewound to where
+        the reference's early-stopping loop would have left it: same edges, same later draws."""
         r_index = self.r_ids.index(r_id)
         for i in range(len(components)):
             comp1 = components[i]
@@ -358,14 +387,21 @@ class DecoupledPRM:
                 comp2 = components[j]
                 if not comp2:
                     continue
-                connecting_pairs = []
-                tries = 0
                 if len(comp1) * len(comp2) > n_pairs:
-                    while len(connecting_pairs) < n_pairs and tries < max_tries:
-                        node1, node2 = random.choice(comp1), random.choice(comp2)
-                        if self.is_collision_free_edge(node1.q, node2.q, r_id):
-                            connecting_pairs.append((node1, node2))
-                        tries += 1
+                    state = random.getstate()
+                    draws = [(random.choice(comp1), random.choice(comp2)) for _ in range(max_tries)]
+                    free = self._segments_free(r_index, [a.q for a, _ in draws], [b.q for _, b in draws])
+                    connecting_pairs, used = [], 0
+                    for (a, b), ok in zip(draws, free):
+                        if len(connecting_pairs) >= n_pairs:
+                            break
+                        used += 1
+                        if ok:
+                            connecting_pairs.append((a, b))
+                    random.setstate(state)
+                    for _ in range(used):
+                        random.choice(comp1)
+                        random.choice(comp2)
                 else:
                     pairs = [(a, b) for a in comp1 for b in comp2]
                     free = self._segments_free(r_index, [a.q for a, _ in pairs], [b.q for _, b in pairs])

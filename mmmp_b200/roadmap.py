@@ -161,3 +161,11 @@ class RoadmapBuilder:
         out = self.candidates(q64, q32)
         out["q64"], out["q32"] = q64, q32
         return out
+
+    def components(self, out):
+        """Connected components of the collision-free candidate graph of build() / candidates()
+        (gathered tables): labels [n] int32 (smallest node id of the component), component count.
+        compute_connected_components (decoupled_prm.py:613-636) on the GPU."""
+        labels, count = core.connected_components(out["idx"], out["edge_free"])
+        self._mark("components")
+        return labels, count

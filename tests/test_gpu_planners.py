@@ -276,3 +276,110 @@ def test_coupled_panda_knn_prm(cuda):
     np.fill_diagonal(D, np.inf)
     assert np.abs(np.sort(D, 1)[:, :6] - prm.last_candidates["dist"]).max() < 1e-12
     assert all(i in prm.roadmap[j] for i in prm.roadmap for j in prm.roadmap[i])
+
+
+# ------------------------------------------------------------------ connected components
+def _host_components(n, edges):
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for a, b in edges:
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    return np.array([find(i) for i in range(n)])
+
+
+def test_connected_components_kernel_vs_union_find(cuda, golden):
+    from mmmp_b200 import core
+    rng = np.random.default_rng(5)
+    for n, cap, p_edge in ((1, 3, 0.5), (257, 2, 0.3), (5000, 3, 0.25), (200000, 4, 0.12)):
+        adj = rng.integers(0, n, size=(n, cap)).astype(np.int32)
+        adj[rng.random((n, cap)) < 0.2] = -1                       # padding
+        mask = (rng.random((n, cap)) < p_edge).astype(np.uint8)
+        labels, count = core.connected_components(torch.from_numpy(adj).to(cuda), torch.from_numpy(mask).to(cuda))
+        ii, cc = np.nonzero((adj >= 0) & (mask > 0))
+        want = _host_components(n, zip(ii.tolist(), adj[ii, cc].tolist()))
+        got = labels.cpu().numpy()
+        assert (got == want).all()                                  # label = smallest node id of the component
+        assert count == len(np.unique(want))
+        labels2, count2 = core.connected_components(torch.from_numpy(np.where(mask > 0, adj, -1).astype(np.int32)).to(cuda))
+        assert (labels2.cpu().numpy() == want).all() and count2 == count      # mask folded into the padding
+    # the reference's prebuilt 766-node roadmap: components of its adjacency lists
+    g = golden("roadmap_766")
+    deg, flat = g["deg"], g["adj"]
+    off = np.concatenate([[0], np.cumsum(deg)])
+    adj = np.full((766, int(deg.max())), -1, dtype=np.int32)
+    for i in range(766):
+        adj[i, :deg[i]] = flat[off[i]:off[i + 1]]
+    labels, count = core.connected_components(torch.from_numpy(adj).to(cuda))
+    want = _host_components(766, [(i, int(j)) for i in range(766) for j in flat[off[i]:off[i + 1]]])
+    assert (labels.cpu().numpy() == want).all() and count == len(np.unique(want))
+
+
+def test_component_stitching_equals_the_sequential_loop(cuda):
+    """compute_connected_components (GPU labels for large roadmaps) and the batched
+    connect_connected_components_random reproduce the reference's sequential loops
+    (decoupled_prm.py:613-704): same components, same added edges, same generator state."""
+    import random
+    from mmmp_b200.planners.prm.pybullet.decoupled.decoupled_prm import DecoupledPRM
+    env = _panda_env(1)
+    prm = DecoupledPRM(env, maxdist=0, k1=2, k2=1, build_type='n', prm_type='degree', n=1, t=1, time_step=0.1,
+                       local_step=0.05)
+    r_id = prm.r_ids[0]
+    prm.add_nodes_robot(r_id, 400)
+    prm.clear_edges(r_id)
+    prm.connect_nearest_neighbors_degree(r_id)
+    r_index = 0
+    base_edges = {k: list(v) for k, v in prm.edge_dicts[r_index].items()}
+    dfs = prm.compute_connected_components(r_id)
+    prm.GPU_COMPONENTS_MIN_NODES = 1                                 # force the GPU path
+    gpu = prm.compute_connected_components(r_id)
+    assert [sorted(n.id for n in c) for c in gpu] == [sorted(n.id for n in c) for c in dfs]
+    assert [c[0].id for c in gpu] == [c[0].id for c in dfs]         # components start at the same node
+    assert len(dfs) > 3
+
+    def sequential(components, n_pairs, max_tries):                  # the reference's loop, one check per try
+        for i in range(len(components)):
+            comp1 = components[i]
+            if not comp1:
+                continue
+            for j in range(i + 1, len(components)):
+                comp2 = components[j]
+                if not comp2:
+                    continue
+                pairs, tries = [], 0
+                if len(comp1) * len(comp2) > n_pairs:
+                    while len(pairs) < n_pairs and tries < max_tries:
+                        a, b = random.choice(comp1), random.choice(comp2)
+                        if prm.is_collision_free_edge(a.q, b.q, r_id):
+                            pairs.append((a, b))
+                        tries += 1
+                else:
+                    for a in comp1:
+                        for b in comp2:
+                            if prm.is_collision_free_edge(a.q, b.q, r_id):
+                                pairs.append((a, b))
+                for a, b in pairs:
+                    prm.edge_dicts[r_index][a.id].append(b.id)
+                    prm.edge_dicts[r_index][b.id].append(a.id)
+                if pairs:
+                    comp1.extend(comp2)
+                    components[j] = []
+        return [c for c in components if c]
+
+    random.seed(1234)
+    seq = sequential([list(c) for c in dfs], 5, 20)
+    seq_edges = {k: list(v) for k, v in prm.edge_dicts[r_index].items()}
+    seq_state = random.getstate()
+    prm.edge_dicts[r_index] = {k: list(v) for k, v in base_edges.items()}
+    random.seed(1234)
+    bat = prm.connect_connected_components_random([list(c) for c in dfs], r_id, n_pairs=5, max_tries=20)
+    assert prm.edge_dicts[r_index] == seq_edges
+    assert [[n.id for n in c] for c in bat] == [[n.id for n in c] for c in seq]
+    assert random.getstate() == seq_state

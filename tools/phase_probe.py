@@ -55,3 +55,6 @@ timed("collide_edges (obst only)", lambda: world.collide_edges(free32, edges, 50
 eh2 = timed("collide_edges exhaustive", lambda: world.collide_edges(free32, edges, 50, 0.02, 0, F | 16))
 print("verdict mismatches vs exhaustive", int((eh2 != eh).sum()))
 fk = timed("fk_chain", lambda: world.fk(free32, 0))
+free_tab = (eh == 0).to(torch.uint8).reshape(ridx.shape)
+labels, count = timed("connected_components (1 M x 10)", lambda: core.connected_components(ridx, free_tab))
+print("components", count, "largest", int(torch.bincount(labels.long()).max()))
