@@ -357,6 +357,23 @@ int mmmp_greedy_degree_connect(const int32_t* nbr_idx_h, const uint8_t* edge_fre
 int mmmp_connected_components(const int32_t* adj_d, const uint8_t* mask_d, int64_t N, int cap,
                               int32_t* labels_d, int64_t* n_components_d, void* stream);
 
+/* Batched inverse kinematics for the task-space sampler:
+ * Panda.solve_closest_arm_ik (robots/panda.py:207-208 -> utils/ik_utils.py:25-27
+ * -> pybullet.calculateInverseKinematics) as called by sample_valid_in_task_space
+ * (decoupled_prm.py:323-344).  Damped least squares on the geometric Jacobian of
+ * the tip frame (frame n_joints * origin[n_joints]), one problem per thread:
+ * dq = J^T (J J^T + lambda^2 I)^-1 e, |dq|_inf <= max_step, joints clamped to
+ * [lo_h, hi_h], until |e_pos| < tol_pos and |e_rot| < tol_rot or max_iters.
+ * target_pos_d [N,3], target_quat_d [N,4] (x,y,z,w; NULL = position only),
+ * q0_d [N, ld0] start configurations (ld0 = 0: one row for all), q_out_d [N, ld]
+ * fp64 (not rounded), converged_d [N] (may be NULL), residual_d [N,2] = final
+ * |e_pos|, |e_rot| (may be NULL).  Parity with pybullet's own solver is
+ * unpinned (pybullet absent); pinned against oracle/ik.py.                  */
+int mmmp_ik_dls(const mmmp_world* w, int robot, const double* target_pos_d, const double* target_quat_d,
+                const double* q0_d, int ld0, int64_t N, const double* lo_h, const double* hi_h,
+                int max_iters, double lambda, double tol_pos, double tol_rot, double max_step,
+                double* q_out_d, int ld, uint8_t* converged_d, float* residual_d, void* stream);
+
 /* library / device introspection */
 int mmmp_version(void);
 int mmmp_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmmmp_b200.so")
 SOURCES = ["world.cu", "sample.cu", "fk.cu", "collide.cu", "planar.cu", "knn_scan.cu", "knn.cu", "components.cu",
-           "host_api.cu"]
+           "ik.cu", "host_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

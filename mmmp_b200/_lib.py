@@ -124,6 +124,7 @@ SIGNATURES = {
     "mmmp_version": [],
     "mmmp_device_info": [_P, _P, _P, _P],
     "mmmp_connected_components": [_P, _P, _I64, _I, _P, _P, _P],
+    "mmmp_ik_dls": [_P, _I, _P, _P, _P, _I, _I64, _P, _P, _I, _D, _D, _D, _D, _P, _I, _P, _P, _P],
     "mmmp_launch_count": [],
 }
 _RESTYPES = {"mmmp_launch_count": C.c_int64}

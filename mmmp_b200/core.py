@@ -493,6 +493,31 @@ class SpatialWorld(_World):
                   _stream())
         return pos
 
+    def ik(self, target_pos: torch.Tensor, target_quat: Optional[torch.Tensor], q0: torch.Tensor, robot: int = 0,
+           max_iters: int = 100, damping: float = 0.05, tol_pos: float = 1e-4, tol_rot: float = 1e-3,
+           max_step: float = 0.3):
+        """Batched damped-least-squares IK of the tip frame (mmmp_ik_dls).  target_pos [N,3] fp64,
+        target_quat [N,4] (x,y,z,w) fp64 or None, q0 [N,D] or [1,D] fp64 start configurations.
+        -> (q [N,D] fp64, converged [N] uint8, residual [N,2] fp32 = |e_pos|, |e_rot|)."""
+        target_pos = _dev(target_pos, torch.float64)
+        q0 = _dev(q0, torch.float64)
+        N, D = target_pos.shape[0], self.robots[robot].model["n_joints"]
+        if target_quat is not None:
+            target_quat = _dev(target_quat, torch.float64)
+            if tuple(target_quat.shape) != (N, 4):
+                raise MmmpError("ik: target_quat must be [N, 4]")
+        if target_pos.shape[1] != 3 or q0.shape[1] != D or q0.shape[0] not in (1, N):
+            raise MmmpError("ik: target_pos must be [N, 3], q0 [N, D] or [1, D]")
+        lim = np.ascontiguousarray(self.robots[robot].model["joint_limits"], dtype=np.float64)
+        lo, hi = np.ascontiguousarray(lim[:, 0]), np.ascontiguousarray(lim[:, 1])
+        q = torch.empty((N, D), dtype=torch.float64, device=target_pos.device)
+        conv = torch.empty((N,), dtype=torch.uint8, device=target_pos.device)
+        res = torch.empty((N, 2), dtype=torch.float32, device=target_pos.device)
+        _lib.call("mmmp_ik_dls", self.handle, robot, _ptr(target_pos), _ptr(target_quat), _ptr(q0),
+                  0 if q0.shape[0] == 1 and N != 1 else D, N, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                  max_iters, damping, tol_pos, tol_rot, max_step, _ptr(q), D, _ptr(conv), _ptr(res), _stream())
+        return q, conv, res
+
     def metric_groups(self, robot: int = 0):
         frames = (C.c_int32 * _lib.MAX_GROUPS)()
         weights = (C.c_float * _lib.MAX_GROUPS)()

@@ -9,11 +9,13 @@ pybullet queries are replaced by batched kernels behind the C ABI:
   is_collision_free_edge (all)  -> mmmp_collide_edges
   greedy accept pass            -> mmmp_greedy_degree_connect (native host replay)
 
-Deviations from the reference, all outside the hot path: samples come from the
-joint-space sampler (reference :310-321) instead of the task-space IK sampler (:323-344),
-because IK lives inside pybullet; start/goal neighbourhood samples
-are joint-space perturbations for the same reason; the random stream is the library's
-Philox generator seeded by the extra `seed` argument.
+Deviations from the reference, all outside the hot path: by default samples come from the
+joint-space sampler (reference :310-321); `sampler='task'` selects the reference's task-space
+sampler (:323-344) with the batched damped-least-squares IK kernel (mmmp_ik_dls) in place of
+pybullet's IK (same sampled tool positions, joint values not pinned against pybullet --
+SURVEY.md 8f rank 4); start/goal neighbourhood samples are joint-space perturbations; the
+joint-space random stream is the library's Philox generator seeded by the extra `seed`
+argument.
 """
 from __future__ import annotations
 
@@ -54,7 +56,10 @@ def safe_poses():
 
 class DecoupledPRM:
     def __init__(self, environment, load_roadmap=None, maxdist=0, k1=0, k2=0, build_type='n', prm_type='degree',
-                 n=0, t=0, time_step=0., local_step=0., seed=0) -> None:
+                 n=0, t=0, time_step=0., local_step=0., seed=0, sampler='joint') -> None:
+        if sampler not in ('joint', 'task'):
+            raise ValueError("sampler must be 'joint' (decoupled_prm.py:310-321) or 'task' (:323-344)")
+        self.sampler = sampler
         self.env = environment
         self.agents = environment.agents
         self.robot_models = environment.robot_models
@@ -165,7 +170,8 @@ class DecoupledPRM:
         r_index = self.r_ids.index(r_id)
         if self.build_type == 't':
             raise NotImplementedError("Update roadmap based on time is not implemented.")
-        samples = self.sample_valid_in_joint_space_random(self.n, r_id)
+        samples = (self.sample_valid_in_task_space(self.n, r_id) if self.sampler == 'task'
+                   else self.sample_valid_in_joint_space_random(self.n, r_id))
         self._append_nodes(r_index, samples)
         if self.prm_type == 'degree':
             self.connect_nearest_neighbors_degree(r_id)
@@ -200,7 +206,57 @@ class DecoupledPRM:
         q = torch.cat(got, 0)[:n].cpu().numpy()
         return [row for row in q]
 
-    sample_valid_in_task_space = sample_valid_in_joint_space_random   # IK sampler: out of scope
+
+    def sample_task_space_position(self, start_pos, goal_pos, k=1, mu=0.4, sigma=0.2):
+        """:346-369, same draws from numpy's global stream in the same order (t, chi-square, theta)."""
+        start_pos, goal_pos = np.array(start_pos, dtype=float), np.array(goal_pos, dtype=float)
+        W = goal_pos - start_pos
+        W /= np.linalg.norm(W)
+        U = np.array([0., 1., 0.]) if np.allclose(W, [1., 0., 0.]) else np.array([1., 0., 0.])
+        U -= np.dot(U, W) * W
+        U /= np.linalg.norm(U)
+        V = np.cross(W, U)
+        t = np.random.uniform(0, 1)
+        d = mu / k * (sigma ** 2 / (2 * k)) ** (1 / 2) * np.random.chisquare(k)
+        theta = np.random.uniform(0, 2 * np.pi)
+        return start_pos + t * (goal_pos - start_pos) + d * (np.cos(theta) * U + np.sin(theta) * V)
+
+    def sample_valid_in_task_space(self, n, r_id, batch=None):
+        """:323-344: positions in a tube around the start-goal segment of the tool, tool pointing
+        down (quaternion of Euler (180 deg, 0, 0)), closest IK from the start pose, rounded to 2 dp,
+        kept when collision free.  The reference solves one pose per pybullet call; here a batch
+        of positions is drawn ahead (same global numpy stream, rewound to what the one-at-a-time
+        loop would have consumed), solved by ONE mmmp_ik_dls launch and checked by one
+        collision launch.  pybullet's IK arithmetic is not available: joint values differ from
+        the reference's (parity unpinned), the sampled tool positions do not."""
+        r_index = self.r_ids.index(r_id)
+        model = self.robot_models[r_index]
+        start = np.asarray(self.agents[r_index]['start'], dtype=float)[:7]
+        goal = np.asarray(self.agents[r_index]['goal'], dtype=float)[:7]
+        start_pos, goal_pos = model.position_from_fk(start), model.position_from_fk(goal)
+        quat = (1.0, 0.0, 0.0, 0.0)                               # p.getQuaternionFromEuler([pi, 0, 0])
+        dev = core._require_cuda()
+        q0 = torch.tensor(start[None], dtype=torch.float64, device=dev)
+        samples = []
+        while len(samples) < n:
+            m = int(batch or max(64, 2 * (n - len(samples))))
+            state = np.random.get_state()
+            pos = np.array([self.sample_task_space_position(start_pos, goal_pos) for _ in range(m)])
+            tq = torch.tensor(np.tile(quat, (m, 1)), dtype=torch.float64, device=dev)
+            q, _, _ = self.env.world.ik(torch.tensor(pos, dtype=torch.float64, device=dev), tq, q0, r_index)
+            q = np.round(q.cpu().numpy(), 2)
+            free = ~self._configs_hit(r_index, q, self._flags())
+            used = 0
+            for qi, ok in zip(q, free):
+                if len(samples) >= n:
+                    break
+                used += 1
+                if ok:
+                    samples.append(qi)
+            np.random.set_state(state)
+            for _ in range(used):
+                self.sample_task_space_position(start_pos, goal_pos)
+        return samples
 
     def sample_safe_poses(self, r_id, sigma=0.2):
         return safe_poses()

@@ -94,12 +94,30 @@ class Panda(Robot):
     def orientation_from_fk(self, q):
         return self.forward_kinematics(q)[:3, :3]
 
-    # inverse kinematics lives inside pybullet in the reference (utils/ik_utils.py:21-27):
-    # out of scope of the roadmap-construction path
-    def solve_arm_ik(self, targetPose):
-        raise NotImplementedError("pybullet IK is outside the roadmap-construction path")
+    # inverse kinematics (panda.py:204-225).  The reference hands these to
+    # pybullet.calculateInverseKinematics (utils/ik_utils.py:21-27); here they run the batched
+    # damped-least-squares kernel (mmmp_ik_dls) on a private single-robot world.  Parity with
+    # pybullet's solver is unpinned.
+    def _ik_world(self):
+        if getattr(self, "_ik_w", None) is None:
+            base = core.base_matrix(self.base_position, self.base_orientation)
+            self._ik_w = core.SpatialWorld([core.RobotSpec(self.model, base, 0)], [])
+        return self._ik_w
 
-    solve_closest_arm_ik = solve_ik = solve_arm_ik
+    def solve_closest_arm_ik(self, targetPose, initialJointPositions):
+        import torch
+        pos, quat = targetPose
+        dev = core._require_cuda()
+        q, conv, _ = self._ik_world().ik(torch.tensor([list(pos)], dtype=torch.float64, device=dev),
+                                         torch.tensor([list(quat)], dtype=torch.float64, device=dev),
+                                         torch.tensor([list(initialJointPositions)[:7]], dtype=torch.float64, device=dev))
+        return tuple(q[0].cpu().tolist())
+
+    def solve_arm_ik(self, targetPose):
+        return self.solve_closest_arm_ik(targetPose, self.get_arm_pose())
+
+    def solve_ik(self, target_position, target_orientation, default_joint_positions):
+        return self.solve_closest_arm_ik((target_position, target_orientation), default_joint_positions)
 
     # distance metrics (panda.py:227-259) -----------------------------------------------
     def distance_metric(self, q1, q2):

@@ -438,3 +438,41 @@ def test_roadmap_candidates_host_end_to_end(core, panda_model, cuda):
         eref = ~ck.edge_collision(qa, qb, 50, 0.02, 0)
         assert (out["edge_free"][sel].ravel().astype(bool) != eref).sum() <= 3
         assert out["timings_ms"][7] > 0
+
+
+# --------------------------------------------------------------------- (8f-4) batched IK
+def test_ik_kernel_vs_float64_oracle(core, panda_model, cuda):
+    """mmmp_ik_dls against the float64 restatement of the same iteration (oracle/ik.py): same
+    convergence verdicts, residuals below tolerance, joint values equal to 2e-3 rad where the
+    iteration is contractive; position-only and full-pose targets; shared start row."""
+    from oracle import chain, ik, spheres
+    base = core.base_matrix((0.1, -0.2, 0.01), (0, 0, 0.38268343, 0.92387953))
+    w = core.SpatialWorld([core.RobotSpec(panda_model, base)], [])
+    rng = np.random.default_rng(31)
+    n = 3000
+    q_true = rng.uniform(LIMITS[:, 0] * 0.6, LIMITS[:, 1] * 0.6, (n, 7))
+    q_true[:, 3] = rng.uniform(-2.4, -0.8, n)
+    F = chain.chain_frames(spheres.model_origins(panda_model), q_true, base)[:, -1]
+    q0 = np.clip(q_true + rng.normal(0, 0.2, q_true.shape), LIMITS[:, 0], LIMITS[:, 1])
+    R = F[:, :3, :3]
+    qw = np.sqrt(np.maximum(1 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2], 1e-12)) / 2
+    quat = np.stack([(R[:, 2, 1] - R[:, 1, 2]) / (4 * qw), (R[:, 0, 2] - R[:, 2, 0]) / (4 * qw),
+                     (R[:, 1, 0] - R[:, 0, 1]) / (4 * qw), qw], 1)
+    tp = core.to_device_f64(np.ascontiguousarray(F[:, :3, 3]))
+    for tq_np in (None, quat):
+        tq = None if tq_np is None else core.to_device_f64(tq_np)
+        q, conv, res = w.ik(tp, tq, core.to_device_f64(q0), 0, max_iters=150)
+        q, conv, res = q.cpu().numpy(), conv.cpu().numpy().astype(bool), res.cpu().numpy()
+        q_ref, ok_ref, res_ref = ik.ik_dls(panda_model, base, F[:, :3, 3], tq_np, q0, max_iters=150)
+        assert conv.mean() > 0.97 and (conv == ok_ref).mean() > 0.995
+        both = conv & ok_ref
+        assert res[both, 0].max() < 1e-4 and res[both, 1].max() < 1e-3
+        # the tool pose of the answer, recomputed in float64, meets the target
+        e, _ = ik.task_error(panda_model, base, q[both], F[both, :3, 3], None if tq_np is None else tq_np[both])
+        assert np.linalg.norm(e[:, :3], axis=1).max() < 2e-4
+        assert np.abs(q[both] - q_ref[both]).max() < (2e-3 if tq_np is not None else 5e-2)
+        assert ((q >= LIMITS[:, 0] - 1e-6) & (q <= LIMITS[:, 1] + 1e-6)).all()
+    # one start row for all problems (ld0 = 0), unreachable targets are reported, not faked
+    far = np.tile([[3.0, 0.0, 0.5]], (5, 1))
+    q, conv, res = w.ik(core.to_device_f64(far), None, core.to_device_f64(q0[:1]), 0, max_iters=50)
+    assert not conv.cpu().numpy().any() and res.cpu().numpy()[:, 0].min() > 1.0

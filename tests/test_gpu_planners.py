@@ -383,3 +383,61 @@ def test_component_stitching_equals_the_sequential_loop(cuda):
     assert prm.edge_dicts[r_index] == seq_edges
     assert [[n.id for n in c] for c in bat] == [[n.id for n in c] for c in seq]
     assert random.getstate() == seq_state
+
+
+# ------------------------------------------------------------------ task-space sampler
+def test_task_space_sampler(cuda, golden):
+    """sample_task_space_position draws exactly what the reference draws (golden = the reference's
+    own function); sample_valid_in_task_space returns collision-free, 2-dp configurations whose
+    tool sits on the sampled positions (IK residual + rounding), pointing down, and leaves numpy's
+    global stream where the reference's one-pose-at-a-time loop would have left it."""
+    from mmmp_b200.planners.prm.pybullet.decoupled.decoupled_prm import DecoupledPRM
+    from oracle import ik
+    g = golden("task_space_sampler")
+    env = _panda_env(1)
+    prm = DecoupledPRM(env, maxdist=0, k1=4, k2=3, build_type='n', prm_type='degree', n=1, t=1, time_step=0.1,
+                       local_step=0.05)
+    for c in range(3):
+        np.random.seed(100 + c)
+        got = np.array([prm.sample_task_space_position(g[f"start{c}"], g[f"goal{c}"]) for _ in range(200)])
+        assert np.abs(got - g[f"pos{c}"]).max() < 1e-12
+    r_id = prm.r_ids[0]
+    model = prm.robot_models[0]
+    np.random.seed(7)
+    samples = np.array(prm.sample_valid_in_task_space(60, r_id, batch=32))
+    state_after = np.random.get_state()
+    assert samples.shape == (60, 7) and (samples == np.round(samples, 2)).all()
+    assert not prm._configs_hit(0, samples, prm._flags()).any()
+    # replay the reference's loop on the same stream: one position per try, accepted in order
+    np.random.seed(7)
+    start, goal = np.asarray(env.agents[0]['start'])[:7], np.asarray(env.agents[0]['goal'])[:7]
+    sp, gp = model.position_from_fk(start), model.position_from_fk(goal)
+    base = core_base(model)
+    accepted, tries = [], 0
+    while len(accepted) < 60:
+        pos = prm.sample_task_space_position(sp, gp)
+        tries += 1
+        q, ok, _ = ik.ik_dls(model.model, base, pos[None], np.array([[1.0, 0, 0, 0]]), start[None])
+        q = np.round(q[0], 2)
+        if not prm._configs_hit(0, q, prm._flags())[0]:
+            accepted.append((pos, q, bool(ok[0])))
+    assert all(a == b for a, b in zip(np.random.get_state()[1].tolist(), state_after[1].tolist()))
+    # the GPU sampler accepted the same tries; joint values agree with the float64 restatement
+    ref_q = np.array([q for _, q, _ in accepted])
+    conv = np.array([o for _, _, o in accepted])
+    assert conv.mean() > 0.8
+    assert np.abs(samples - ref_q)[conv].max() <= 0.011            # 2-dp rounding of fp32 vs fp64 iterates
+    tool = np.array([model.position_from_fk(q) for q in samples])
+    want = np.array([p for p, _, _ in accepted])
+    assert np.linalg.norm(tool - want, axis=1)[conv].max() < 0.02  # 0.005 rad rounding x ~1 m reach
+    down = np.array([model.orientation_from_fk(q)[:, 2] for q in samples])
+    assert (down[conv, 2] < -0.99).all()                           # tool z axis points down (Euler 180, 0, 0)
+    # the planner builds from this sampler when asked to
+    prm2 = DecoupledPRM(env, maxdist=0, k1=4, k2=3, build_type='n', prm_type='degree', n=40, t=1, time_step=0.1,
+                        local_step=0.05, sampler='task')
+    assert len(prm2.node_lists[0]) >= 40
+
+
+def core_base(model):
+    from mmmp_b200 import core
+    return core.base_matrix(model.base_position, model.base_orientation)

@@ -150,3 +150,39 @@ def test_hull_oracle_known_answers():
     d_local = hull.posed_distance(H[5], np.eye(4)[None], H[7], (np.linalg.inv(TA[0]) @ TB[0])[None])[0]
     assert d_world == pytest.approx(d_local, abs=1e-9) and d_world == pytest.approx(0.01106909, abs=1e-7)
     assert not hull.PandaHullChecker([core.base_matrix((0, 0, 0.01))]).self_collision(q)[0]
+
+
+def test_task_space_position_sampler_matches_reference(golden):
+    """oracle.ik.task_space_positions restates sample_task_space_position (decoupled_prm.py:346-369);
+    golden = the reference's own function under a seeded numpy stream + the draws it consumed."""
+    from oracle import ik
+    g = golden("task_space_sampler")
+    for c in range(3):
+        d = g[f"draws{c}"]
+        got = ik.task_space_positions(g[f"start{c}"], g[f"goal{c}"], d[:, 0], d[:, 1], d[:, 2])
+        assert np.abs(got - g[f"pos{c}"]).max() < 1e-12
+
+
+def test_ik_oracle_reaches_reachable_poses():
+    """The float64 DLS restatement converges on poses generated by FK (known to be reachable)."""
+    from mmmp_b200 import core
+    from oracle import ik, spheres
+    model = core.load_model("panda_spheres")
+    base = core.base_matrix((0.1, -0.2, 0.01), (0, 0, 0.38268343, 0.92387953))
+    lim = np.array(model["joint_limits"])
+    rng = np.random.default_rng(3)
+    q_true = rng.uniform(lim[:, 0] * 0.6, lim[:, 1] * 0.6, (40, 7))
+    q_true[:, 3] = rng.uniform(-2.4, -0.8, 40)
+    F = chain.chain_frames(spheres.model_origins(model), q_true, base)[:, -1]
+    q0 = np.clip(q_true + rng.normal(0, 0.25, q_true.shape), lim[:, 0], lim[:, 1])
+    q, ok, res = ik.ik_dls(model, base, F[:, :3, 3], None, q0)
+    assert ok.all() and res[:, 0].max() < 1e-4
+    # with orientation: target quaternion from the rotation matrices
+    R = F[:, :3, :3]
+    w = np.sqrt(np.maximum(1 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2], 1e-12)) / 2
+    quat = np.stack([(R[:, 2, 1] - R[:, 1, 2]) / (4 * w), (R[:, 0, 2] - R[:, 2, 0]) / (4 * w),
+                     (R[:, 1, 0] - R[:, 0, 1]) / (4 * w), w], 1)
+    assert np.abs(ik.quat_to_rot(quat) - R).max() < 1e-9
+    q, ok, res = ik.ik_dls(model, base, F[:, :3, 3], quat, q0, max_iters=200)
+    assert ok.mean() > 0.9 and res[ok].max() < 1e-3
+    assert ((q >= lim[:, 0] - 1e-12) & (q <= lim[:, 1] + 1e-12)).all()

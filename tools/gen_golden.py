@@ -20,6 +20,7 @@ CODE on seeded inputs:
   scipy_knn.npz          res/images/{random,halton}_samples.csv and their k=5 / r=0.2 roadmaps
   roadmap_766.npz        res/images/task_space_roadmap2_adjusted_pruned.csv parsed by the
                          reference's own utils/pb_data_utils.load_roadmap
+  task_space_sampler.npz DecoupledPRM.sample_task_space_position outputs + the draws it consumed
 """
 import os
 import sys
@@ -359,11 +360,36 @@ def gen_fixtures():
     print("fixtures: 766-roadmap nodes", len(keys), "directed edges", len(adj))
 
 
+def gen_task_space_sampler():
+    """DecoupledPRM.sample_task_space_position (decoupled_prm.py:346-369), called unbound (it
+    does not touch self) under a seeded numpy global stream; the draws it consumed are
+    recovered by replaying the same stream (uniform, chisquare(1), uniform per sample)."""
+    from planners.prm.pybullet.decoupled.decoupled_prm import DecoupledPRM
+    out = {}
+    cases = [((0.31, -0.2, 0.45), (0.55, 0.35, 0.3)), ((0.2, 0.0, 0.5), (0.7, 0.0, 0.5)),   # second: W = +x
+             ((-0.4, 0.3, 0.2), (0.1, -0.5, 0.8))]
+    for c, (start, goal) in enumerate(cases):
+        np.random.seed(100 + c)
+        pos = np.array([DecoupledPRM.sample_task_space_position(None, start, goal) for _ in range(200)])
+        np.random.seed(100 + c)
+        draws = np.array([[np.random.uniform(0, 1), np.random.chisquare(1), np.random.uniform(0, 2 * np.pi)]
+                          for _ in range(200)])
+        out[f"start{c}"], out[f"goal{c}"], out[f"pos{c}"], out[f"draws{c}"] = np.array(start), np.array(goal), pos, draws
+    np.savez_compressed(os.path.join(OUT, "task_space_sampler.npz"), **out)
+    print("task-space sampler: first position", out["pos0"][0])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     patches = install_stubs()
     sys.path.insert(0, REF)
     os.chdir(REF)
-    gen_planar(patches)
-    gen_panda()
-    gen_fixtures()
+    only = sys.argv[1:]
+    if not only or "planar" in only:
+        gen_planar(patches)
+    if not only or "panda" in only:
+        gen_panda()
+    if not only or "fixtures" in only:
+        gen_fixtures()
+    if not only or "task_space" in only:
+        gen_task_space_sampler()

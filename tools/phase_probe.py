@@ -58,3 +58,9 @@ fk = timed("fk_chain", lambda: world.fk(free32, 0))
 free_tab = (eh == 0).to(torch.uint8).reshape(ridx.shape)
 labels, count = timed("connected_components (1 M x 10)", lambda: core.connected_components(ridx, free_tab))
 print("components", count, "largest", int(torch.bincount(labels.long()).max()))
+# batched IK: tool positions of the free nodes as targets, tool pointing down, one shared start pose
+tip = fk[:, -1, :].double().contiguous()
+quat = torch.tensor([[1.0, 0.0, 0.0, 0.0]], dtype=torch.float64, device=tip.device).repeat(tip.shape[0], 1)
+q_start = torch.tensor([[0.0, -0.785, 0.0, -2.356, 0.0, 1.571, 0.785]], dtype=torch.float64, device=tip.device)
+qi, conv, res = timed("ik_dls 1 M poses (<= 100 iterations)", lambda: world.ik(tip, quat, q_start, 0))
+print("ik converged", float(conv.float().mean()))
