@@ -247,9 +247,17 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
 #pragma unroll 1
         for (int j = 0; j < R.n_joints; ++j) {
             const float qj = ql.get(lr, col + j);
+            // MUFU sine/cosine: |error| < 1e-6 on the joint ranges (|q| < 3.8), i.e. a few micrometres
+            // at the tool -- three orders below the sphere-fit margin and inside MMMP_GAP_SLACK;
+            // the accurate sincosf was a quarter of the instructions of a verdict-only evaluation
             float s, c;
+#ifdef MMMP_COLLIDE_ACCURATE_SINCOS
             sincosf(qj, &s, &c);
-            affine_step(T, R.origin[j], s, c);
+#else
+            __sincosf(qj, &s, &c);
+#endif
+            if (R.origin_rx[j]) affine_step_rx(T, R.origin[j], s, c);
+            else affine_step(T, R.origin[j], s, c);
             float* p = fr + (size_t)(slot0 + j) * 12 * stride;
 #pragma unroll
             for (int i = 0; i < 12; ++i) p[i * stride] = T.m[i];

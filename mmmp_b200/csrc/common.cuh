@@ -49,6 +49,8 @@ struct RobotDev {
     int frame_link_begin[MMMP_MAX_JOINTS + 2];   // links of frame f: [begin[f], begin[f+1])
     int link_sphere_begin[MMMP_MAX_LINKS + 1];
     float reach[MMMP_MAX_JOINTS][MMMP_MAX_JOINTS + 1];  // [m][f]: bound of |d centre / d q_m|, frame f
+    int origin_rx[MMMP_MAX_JOINTS + 1];  // 1: origin[j] is a rotation about x plus a translation (mod-DH rows)
+    int pad_rx[3];
     uchar2 self_pair[MMMP_MAX_SELF_PAIRS];
     PairTableDev table[MMMP_MAX_PAIR_TABLES];
     float4 sphere[MMMP_MAX_SPHERES];    // frame local xyz, r (frame-0 links: WORLD xyz)
@@ -119,6 +121,28 @@ __device__ __forceinline__ void affine_step(Affine& T, const float* __restrict__
         r[4 * i + 0] = fmaf(a, O[0], fmaf(b, O[4], d * O[8]));
         r[4 * i + 1] = fmaf(a, O[1], fmaf(b, O[5], d * O[9]));
         r[4 * i + 2] = fmaf(a, O[2], fmaf(b, O[6], d * O[10]));
+        r[4 * i + 3] = fmaf(a, O[3], fmaf(b, O[7], fmaf(d, O[11], T.m[4 * i + 3])));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float x = r[4 * i + 0], y = r[4 * i + 1];
+        T.m[4 * i + 0] = fmaf(x, c, y * s);
+        T.m[4 * i + 1] = fmaf(y, c, -x * s);
+        T.m[4 * i + 2] = r[4 * i + 2];
+        T.m[4 * i + 3] = r[4 * i + 3];
+    }
+}
+
+// Same for an origin of the form [1 0 0 a; 0 ca -sa y; 0 sa ca z] (every modified-DH row): the
+// products with its exact zeros and its exact one are dropped, the result is bit-identical.
+__device__ __forceinline__ void affine_step_rx(Affine& T, const float* __restrict__ O, float s, float c) {
+    float r[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = T.m[4 * i + 0], b = T.m[4 * i + 1], d = T.m[4 * i + 2];
+        r[4 * i + 0] = a;
+        r[4 * i + 1] = fmaf(b, O[5], d * O[9]);
+        r[4 * i + 2] = fmaf(b, O[6], d * O[10]);
         r[4 * i + 3] = fmaf(a, O[3], fmaf(b, O[7], fmaf(d, O[11], T.m[4 * i + 3])));
     }
 #pragma unroll

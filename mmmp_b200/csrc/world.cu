@@ -103,11 +103,15 @@ extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
             R.base[i] = (float)d.base[i];
             R64.base[i] = d.base[i];
         }
-        for (int j = 0; j <= d.n_joints; ++j)
+        for (int j = 0; j <= MMMP_MAX_JOINTS; ++j) R.origin_rx[j] = 0;
+        for (int j = 0; j <= d.n_joints; ++j) {
             for (int i = 0; i < 12; ++i) {
                 R.origin[j][i] = (float)d.origin[j][i];
                 R64.origin[j][i] = d.origin[j][i];
             }
+            const float* O = R.origin[j];
+            R.origin_rx[j] = O[0] == 1.f && O[1] == 0.f && O[2] == 0.f && O[4] == 0.f && O[8] == 0.f;
+        }
         // spheres sorted by link; link_sphere_begin[l] = #spheres with link < l
         for (int l = 0; l <= MMMP_MAX_LINKS; ++l) R.link_sphere_begin[l] = 0;
         int prev = 0;
