@@ -33,8 +33,9 @@ namespace {
 struct SpatialSmem {
     int n_r;
     int n_obs;
-    int slots;                         // frame slots per thread (sum of n_joints)
-    int links;                         // link slots per thread (sum of n_links)
+    int slots;                         // frame slots per thread (stored frames of all robots)
+    int links;                         // link slots per thread (stored bounding-sphere centres)
+    int mode;                          // RobotDev::frame_store / link_store row in use
     int any_tables;
     int col[MMMP_MAX_ROBOTS];          // first column of local robot lr in a q row
     int frame_slot[MMMP_MAX_ROBOTS];   // first frame slot of local robot lr
@@ -49,13 +50,16 @@ struct SpatialArgs {
     uint32_t flags;
     int slots;  // frame slots per thread
     int links;  // link slots per thread
+    int mode;   // 0: only what the self pairs read back; 1: every link (robot-robot tests)
 };
 
 // per-thread shared-memory column, element e of this thread at fr[e * stride]:
-//   [0, 12*slots)                 frame poses (row-major 3x4), slot = frame - 1
-//   [12*slots, +3*links)          world centres of the link bounding spheres
-//   [12*slots + 3*links, +slots)  travel bound of each frame per unit t (edge checks)
-#define MMMP_COLUMN_FLOATS(slots, links) (13 * (slots) + 3 * (links))
+//   [0, 12*slots)                 frame poses (row-major 3x4) of the frames read back later
+//   [12*slots, +3*links)          world centres of the link bounding spheres read back later
+//   [12*slots + 3*links, +slots)  mode 1: travel bound of each stored frame per unit t
+// (RobotDev::frame_store / link_store map frames and links to slots; a Panda checked for self
+// and obstacle collision keeps 6 frames and 6 centres: 360 B per thread, 4 CTAs per SM)
+#define MMMP_COLUMN_FLOATS(slots, links, mode) ((12 + ((mode) ? 1 : 0)) * (slots) + 3 * (links))
 
 // --- q loaders -------------------------------------------------------------
 struct QConfig {
@@ -98,14 +102,15 @@ __device__ __forceinline__ void stage_world(const SpatialArgs& A, unsigned char*
         hdr->n_obs = n_obs;
         hdr->slots = A.slots;
         hdr->links = A.links;
+        hdr->mode = A.mode;
         int slot = 0, lslot = 0, tables = 0;
         for (int lr = 0; lr < A.n_r; ++lr) {
             const RobotDev& R = A.W->robots[A.robots[lr]];
             hdr->col[lr] = A.col[lr];
             hdr->frame_slot[lr] = slot;
             hdr->link_slot[lr] = lslot;
-            slot += R.n_joints;
-            lslot += R.n_links;
+            slot += R.n_frame_store[A.mode];
+            lslot += R.n_link_store[A.mode];
             tables += R.n_tables;
         }
         hdr->any_tables = tables;
@@ -125,13 +130,13 @@ __device__ __forceinline__ void stage_world(const SpatialArgs& A, unsigned char*
 
 // frame f (1..n) of a robot from the thread's shared-memory column; f == 0 is the
 // identity because frame-0 (base link) spheres are stored in world coordinates
-__device__ __forceinline__ void load_frame(Affine& T, const float* fr, int stride, int slot0, int f) {
-    if (f == 0) {
+__device__ __forceinline__ void load_frame(Affine& T, const float* fr, int stride, int slot0, int fslot) {
+    if (fslot < 0) {  // frame 0 (never stored)
 #pragma unroll
         for (int i = 0; i < 12; ++i) T.m[i] = (i == 0 || i == 5 || i == 10) ? 1.f : 0.f;
         return;
     }
-    const float* p = fr + (size_t)(slot0 + f - 1) * 12 * stride;
+    const float* p = fr + (size_t)(slot0 + fslot) * 12 * stride;
 #pragma unroll
     for (int i = 0; i < 12; ++i) T.m[i] = p[i * stride];
 }
@@ -191,20 +196,27 @@ __device__ __forceinline__ bool link_pair_hit(const RobotDev& RA, int la, const 
     return false;
 }
 
+// bit of the pair table P at joint values (qu, qw); no branch, so that look-ups of several
+// steps can be in flight together
+__device__ __forceinline__ unsigned table_bit(const WorldDev* __restrict__ Wg, const PairTableDev& P, float qu,
+                                              float qw) {
+    int iu = (int)floorf((qu - P.lo_u) * P.inv_du);
+    int iv = (int)floorf((qw - P.lo_v) * P.inv_dv);
+    iu = min(max(iu, 0), P.n_u - 1);
+    iv = min(max(iv, 0), P.n_v - 1);
+    const int cell = iu * P.n_v + iv;
+    return (__ldg(Wg->table_bits + P.word_offset + (cell >> 5)) >> (cell & 31)) & 1u;
+}
+
 template <class QL>
 __device__ __forceinline__ bool tables_hit(const WorldDev* __restrict__ Wg, const RobotDev& R, int lr, int col,
                                            const QL& ql) {
+    unsigned hit = 0;
     for (int t = 0; t < R.n_tables; ++t) {
         const PairTableDev& P = R.table[t];
-        const float qu = ql.get(lr, col + P.joint_u), qw = ql.get(lr, col + P.joint_v);
-        int iu = (int)floorf((qu - P.lo_u) * P.inv_du);
-        int iv = (int)floorf((qw - P.lo_v) * P.inv_dv);
-        iu = min(max(iu, 0), P.n_u - 1);
-        iv = min(max(iv, 0), P.n_v - 1);
-        const int cell = iu * P.n_v + iv;
-        if ((__ldg(Wg->table_bits + P.word_offset + (cell >> 5)) >> (cell & 31)) & 1u) return true;
+        hit |= table_bit(Wg, P, ql.get(lr, col + P.joint_u), ql.get(lr, col + P.joint_v));
     }
-    return false;
+    return hit != 0;
 }
 
 // One configuration.  Returns < 0 when it is in collision.  Otherwise: GAP = false returns 1;
@@ -222,6 +234,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
     const float HIT = -1.f;
     const float INF = __int_as_float(0x7f800000);
     const int n_r = hdr->n_r;
+    const int mode = hdr->mode;
     const int n_obs = (flags & MMMP_CHECK_OBSTACLES) ? hdr->n_obs : 0;
     float* cen = fr + (size_t)hdr->slots * 12 * stride;
     float* vel = cen + (size_t)hdr->links * 3 * stride;
@@ -235,10 +248,12 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
         const int slot0 = hdr->frame_slot[lr];
         float* cl = cen + (size_t)hdr->link_slot[lr] * 3 * stride;
         for (int l = R.frame_link_begin[0]; l < R.frame_link_begin[1]; ++l) {  // base links: world coordinates
+            const int ls = R.link_store[mode][l];
+            if (ls < 0) continue;
             const float4 B = R.link_bound[l];
-            cl[(3 * l + 0) * stride] = B.x;
-            cl[(3 * l + 1) * stride] = B.y;
-            cl[(3 * l + 2) * stride] = B.z;
+            cl[(3 * ls + 0) * stride] = B.x;
+            cl[(3 * ls + 1) * stride] = B.y;
+            cl[(3 * ls + 2) * stride] = B.z;
         }
         bool hit = false;
         float adq[MMMP_MAX_JOINTS];
@@ -258,9 +273,12 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
 #endif
             if (R.origin_rx[j]) affine_step_rx(T, R.origin[j], s, c);
             else affine_step(T, R.origin[j], s, c);
-            float* p = fr + (size_t)(slot0 + j) * 12 * stride;
+            const int fs = R.frame_store[mode][j + 1];
+            if (fs >= 0) {
+                float* p = fr + (size_t)(slot0 + fs) * 12 * stride;
 #pragma unroll
-            for (int i = 0; i < 12; ++i) p[i * stride] = T.m[i];
+                for (int i = 0; i < 12; ++i) p[i * stride] = T.m[i];
+            }
             float inv_v = 0.f, want = 0.f;
             if (GAP) {
                 const float dj = fabsf(ql.delta(lr, col + j));
@@ -270,7 +288,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                     if (m == j) adq[m] = dj;
                     if (m <= j) v = fmaf(adq[m], R.reach[m][j + 1], v);
                 }
-                vel[(slot0 + j) * stride] = v;
+                if (mode && fs >= 0) vel[(slot0 + fs) * stride] = v;
                 inv_v = __fdividef(1.f, fmaxf(v, 1e-20f));
                 want = fmaf(v, t_want, MMMP_GAP_SLACK);
             }
@@ -280,9 +298,12 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                 const float4 B = R.link_bound[l];
                 if (B.w < 0.f) continue;
                 const float3 wb = affine_point(T, B.x, B.y, B.z);
-                cl[(3 * l + 0) * stride] = wb.x;
-                cl[(3 * l + 1) * stride] = wb.y;
-                cl[(3 * l + 2) * stride] = wb.z;
+                const int ls = R.link_store[mode][l];
+                if (ls >= 0) {
+                    cl[(3 * ls + 0) * stride] = wb.x;
+                    cl[(3 * ls + 1) * stride] = wb.y;
+                    cl[(3 * ls + 2) * stride] = wb.z;
+                }
                 for (int o = 0; o < n_obs; ++o) {
                     float g = INF;
                     const bool bound_hit = sphere_vs_obstacle<GAP>(wb.x, wb.y, wb.z, B.w, obs[o], g);
@@ -306,9 +327,10 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                 const uchar2 pr = R.self_pair[pi];
                 const int fa = R.link_frame[pr.x], fb = R.link_frame[pr.y];
                 const float ra = R.link_bound[pr.x].w, rb = R.link_bound[pr.y].w;
-                const float dx = cl[(3 * pr.x + 0) * stride] - cl[(3 * pr.y + 0) * stride];
-                const float dy = cl[(3 * pr.x + 1) * stride] - cl[(3 * pr.y + 1) * stride];
-                const float dz = cl[(3 * pr.x + 2) * stride] - cl[(3 * pr.y + 2) * stride];
+                const int sa = R.link_store[mode][pr.x], sb = R.link_store[mode][pr.y];
+                const float dx = cl[(3 * sa + 0) * stride] - cl[(3 * sb + 0) * stride];
+                const float dy = cl[(3 * sa + 1) * stride] - cl[(3 * sb + 1) * stride];
+                const float dz = cl[(3 * sa + 2) * stride] - cl[(3 * sb + 2) * stride];
                 const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 const float rr = ra + rb;
                 float g = INF, v = 0.f, want = 0.f;
@@ -322,8 +344,8 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                 }
                 if (GAP ? g <= want : d2 <= rr * rr) {
                     Affine TA, TB;
-                    load_frame(TA, fr, stride, slot0, fa);
-                    load_frame(TB, fr, stride, slot0, fb);
+                    load_frame(TA, fr, stride, slot0, R.frame_store[mode][fa]);
+                    load_frame(TB, fr, stride, slot0, R.frame_store[mode][fb]);
                     g = INF;
                     if (link_pair_hit<GAP>(R, pr.x, TA, R, pr.y, TB, want, g)) return HIT;
                 }
@@ -342,29 +364,31 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                     const float ra = R1.link_bound[la].w;
                     if (ra < 0.f) continue;
                     const int fa = R1.link_frame[la];
-                    const float ax = c1[(3 * la + 0) * stride], ay = c1[(3 * la + 1) * stride],
-                                az = c1[(3 * la + 2) * stride];
+                    const int sa = R1.link_store[mode][la];
+                    const float ax = c1[(3 * sa + 0) * stride], ay = c1[(3 * sa + 1) * stride],
+                                az = c1[(3 * sa + 2) * stride];
                     for (int lb = 0; lb < R2.n_links; ++lb) {
                         const float rb = R2.link_bound[lb].w;
                         if (rb < 0.f) continue;
                         const int fb = R2.link_frame[lb];
                         if (fa == 0 && fb == 0) continue;  // static pair
-                        const float dx = ax - c2[(3 * lb + 0) * stride], dy = ay - c2[(3 * lb + 1) * stride],
-                                    dz = az - c2[(3 * lb + 2) * stride];
+                        const int sb = R2.link_store[mode][lb];
+                        const float dx = ax - c2[(3 * sb + 0) * stride], dy = ay - c2[(3 * sb + 1) * stride],
+                                    dz = az - c2[(3 * sb + 2) * stride];
                         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                         const float rr = ra + rb;
                         float g = INF, v = 0.f, want = 0.f;
                         if (GAP) {
-                            const float va = fa > 0 ? vel[(hdr->frame_slot[l1] + fa - 1) * stride] : 0.f;
-                            const float vb = fb > 0 ? vel[(hdr->frame_slot[l2] + fb - 1) * stride] : 0.f;
+                            const float va = fa > 0 ? vel[(hdr->frame_slot[l1] + R1.frame_store[mode][fa]) * stride] : 0.f;
+                            const float vb = fb > 0 ? vel[(hdr->frame_slot[l2] + R2.frame_store[mode][fb]) * stride] : 0.f;
                             v = va + vb;
                             want = fmaf(v, t_want, MMMP_GAP_SLACK);
                             g = fast_sqrt(d2) - rr;
                         }
                         if (GAP ? g <= want : d2 <= rr * rr) {
                             Affine TA, TB;
-                            load_frame(TA, fr, stride, hdr->frame_slot[l1], fa);
-                            load_frame(TB, fr, stride, hdr->frame_slot[l2], fb);
+                            load_frame(TA, fr, stride, hdr->frame_slot[l1], R1.frame_store[mode][fa]);
+                            load_frame(TB, fr, stride, hdr->frame_slot[l2], R2.frame_store[mode][fb]);
                             g = INF;
                             if (link_pair_hit<GAP>(R1, la, TA, R2, lb, TB, want, g)) return HIT;
                         }
@@ -545,11 +569,22 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
                     pb = qb_base + e * ld;
                 }
                 if (use_tables && mask) {  // pair tables depend on q alone: look every step up
-                    for (int i = gl; i < n_steps; i += L) {
-                        QEdge ql{pa, pb, (float)((double)i * step)};
-                        for (int lr = 0; lr < hdr->n_r; ++lr)
-                            table_hit |= tables_hit(A.W, robs[lr], lr, hdr->col[lr], ql);
+                    unsigned bits = 0;
+                    for (int lr = 0; lr < hdr->n_r; ++lr) {
+                        const RobotDev& R = robs[lr];
+                        for (int tb = 0; tb < R.n_tables; ++tb) {
+                            const PairTableDev& P = R.table[tb];
+                            const int cu = hdr->col[lr] + P.joint_u, cv = hdr->col[lr] + P.joint_v;
+                            const float au = __ldg(pa + cu), av = __ldg(pa + cv);
+                            const float du = __ldg(pb + cu) - au, dv = __ldg(pb + cv) - av;
+#pragma unroll 4
+                            for (int i = gl; i < n_steps; i += L) {  // independent look-ups: several in flight
+                                const float t = (float)((double)i * step);
+                                bits |= table_bit(A.W, P, fmaf(t, du, au), fmaf(t, dv, av));  // = QEdge::get
+                            }
+                        }
                     }
+                    table_hit = bits != 0;
                 }
             }
         }
@@ -714,17 +749,19 @@ int fill_args(const mmmp_world* w, int robot, uint32_t flags, SpatialArgs& A) {
         A.n_r = 1;
         A.robots[0] = robot;
         A.col[0] = 0;
-        A.slots = H->robots[robot].n_joints;
-        A.links = H->robots[robot].n_links;
+        A.mode = 0;
+        A.slots = H->robots[robot].n_frame_store[0];
+        A.links = H->robots[robot].n_link_store[0];
     } else {
         A.n_r = H->n_robots;
+        A.mode = ((flags & MMMP_CHECK_ROBOTS) && H->n_robots > 1) ? 1 : 0;
         A.slots = 0;
         A.links = 0;
         for (int r = 0; r < H->n_robots; ++r) {
             A.robots[r] = r;
             A.col[r] = H->robots[r].dof_offset;
-            A.slots += H->robots[r].n_joints;
-            A.links += H->robots[r].n_links;
+            A.slots += H->robots[r].n_frame_store[A.mode];
+            A.links += H->robots[r].n_link_store[A.mode];
         }
     }
     return MMMP_OK;
@@ -734,7 +771,7 @@ size_t smem_bytes(const mmmp_world* w, const SpatialArgs& A, int block) {
     size_t off = (sizeof(SpatialSmem) + 15) & ~(size_t)15;
     off += (sizeof(RobotDev) * A.n_r + 15) & ~(size_t)15;
     off += (sizeof(ObstacleDev) * w->spatial_h->n_obstacles + 15) & ~(size_t)15;
-    off += (size_t)MMMP_COLUMN_FLOATS(A.slots, A.links) * sizeof(float) * block;
+    off += (size_t)MMMP_COLUMN_FLOATS(A.slots, A.links, A.mode) * sizeof(float) * block;
     return off;
 }
 
@@ -824,8 +861,9 @@ extern "C" int mmmp_collide_robot_pairs(const mmmp_world* w, int ra, int rb, con
     A.robots[0] = ra;
     A.robots[1] = rb;
     A.col[0] = A.col[1] = 0;
-    A.slots = H->robots[ra].n_joints + H->robots[rb].n_joints;
-    A.links = H->robots[ra].n_links + H->robots[rb].n_links;
+    A.mode = 1;
+    A.slots = H->robots[ra].n_frame_store[1] + H->robots[rb].n_frame_store[1];
+    A.links = H->robots[ra].n_link_store[1] + H->robots[rb].n_link_store[1];
     int block, grid;
     size_t smem;
     int rc = pick_launch(collide_pairs_kernel, w, A, 128, N, block, smem, grid);

@@ -51,6 +51,13 @@ struct RobotDev {
     float reach[MMMP_MAX_JOINTS][MMMP_MAX_JOINTS + 1];  // [m][f]: bound of |d centre / d q_m|, frame f
     int origin_rx[MMMP_MAX_JOINTS + 1];  // 1: origin[j] is a rotation about x plus a translation (mod-DH rows)
     int pad_rx[3];
+    // What a collision thread parks in its shared-memory column, per mode (0: self pairs only,
+    // 1: every link, for robot-robot tests): slot of frame f / of link l's bounding-sphere
+    // centre, -1 = not needed later, not stored.
+    int n_frame_store[2], n_link_store[2];
+    signed char frame_store[2][MMMP_MAX_JOINTS + 2];
+    signed char link_store[2][MMMP_MAX_LINKS];
+    signed char pad_store[4];
     uchar2 self_pair[MMMP_MAX_SELF_PAIRS];
     PairTableDev table[MMMP_MAX_PAIR_TABLES];
     float4 sphere[MMMP_MAX_SPHERES];    // frame local xyz, r (frame-0 links: WORLD xyz)

@@ -239,6 +239,23 @@ extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
                     continue;
                 R.self_pair[R.n_self_pairs++] = make_uchar2((unsigned char)a, (unsigned char)b);
             }
+        // per-thread column layout of the collision kernels: which frames / link centres are read
+        // back after the FK sweep (mode 0: by the self pairs; mode 1: by robot-robot tests too)
+        for (int mode = 0; mode < 2; ++mode) {
+            bool need_link[MMMP_MAX_LINKS] = {false};
+            for (int l = 0; l < d.n_links; ++l)
+                need_link[l] = mode == 1 && R.link_sphere_begin[l + 1] > R.link_sphere_begin[l];
+            for (int p = 0; p < R.n_self_pairs; ++p) need_link[R.self_pair[p].x] = need_link[R.self_pair[p].y] = true;
+            R.n_link_store[mode] = 0;
+            for (int l = 0; l < MMMP_MAX_LINKS; ++l)
+                R.link_store[mode][l] = (l < d.n_links && need_link[l]) ? (signed char)R.n_link_store[mode]++ : (signed char)-1;
+            R.n_frame_store[mode] = 0;
+            for (int f = 0; f < MMMP_MAX_JOINTS + 2; ++f) {
+                bool need = false;
+                for (int l = 0; l < d.n_links; ++l) need = need || (need_link[l] && R.link_frame[l] == f);
+                R.frame_store[mode][f] = (f >= 1 && f <= d.n_joints && need) ? (signed char)R.n_frame_store[mode]++ : (signed char)-1;
+            }
+        }
         if (d.dof_offset + d.n_joints > dof) dof = d.dof_offset + d.n_joints;
     }
     H->dof = dof;
