@@ -333,7 +333,7 @@ def run_ours(args):
         # edge-collision pair.  `roofline` is the scan, reported against HBM as north_star asks, with
         # the ALGORITHMIC streamed bytes of SURVEY.md 8d for an exhaustive scan,
         #     ceil(Nq / Tq) * Nr * Dp * 4 + Nq * kc * 8,
-        # Tq = 128 queries per CTA, Dp = 16 (15-D FK features padded), kc = k + 6 candidates.  The kernel
+        # Tq = 128 queries per CTA, Dp = 16 (15-D FK features padded), kc = k + 2 candidates.  The kernel
         # skips every tile its bounding-box test proves irrelevant and its rows stay in the 126 MB L2,
         # so the fraction can exceed 1: `executed` carries what one launch really moved and evaluated
         # (library counters, read in an untimed launch after the timed region).
@@ -341,7 +341,7 @@ def run_ours(args):
         scan_ms = phases.get("knn_scan", 0.0) / max(n_launch, 1)
         edge_ms = phases.get("edge_collision", 0.0) / max(n_launch, 1)
         nq = (args.nodes + world_size - 1) // world_size
-        TQ, DP, kc = 128, 16, args.k + 6
+        TQ, DP, kc = 128, 16, args.k + 2
         alg_bytes = -(-nq // TQ) * args.nodes * DP * 4 + nq * kc * 8
         pairs = nq * args.nodes
         scan_flops = pairs * (5 * 9 + 5)             # FK-metric pair = 5 groups x 9 flop + 5

@@ -27,6 +27,15 @@ invert_flags_kernel(uint8_t* f, int64_t n) {
         f[i] = f[i] ? 0 : 1;
 }
 
+// *out |= 1 if any byte of f is non-zero
+__global__ void __launch_bounds__(256)
+any_flag_kernel(const uint8_t* __restrict__ f, int64_t n, int* __restrict__ out) {
+    bool any = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        any = any || f[i] != 0;
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(out, 1);
+}
+
 thread_local cudaStream_t tl_alloc_stream = nullptr;  // stream the host call allocates on
 
 struct DevBuf {  // stream-ordered temporaries from the (cached) default pool
@@ -102,7 +111,10 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
     if (metric_kind != MMMP_METRIC_L2 && metric_kind != MMMP_METRIC_GROUP_L2_SUM) return MMMP_ERR_KIND;
     auto row_width = [](int d) { return d <= 4 ? 4 : (d <= 8 ? 8 : (d <= 16 ? 16 : 32)); };
     const int ld32 = row_width(D);
-    int kc = k + 6;
+    // the fp32 scan keeps k + 2 candidates for the fp64 re-rank; if that cannot separate rank k
+    // from the last candidate anywhere (flagged `ambiguous`, ~1e-8 per query) the scan is repeated
+    // once with k + 16
+    int kc = k + 2;
     if (kc > MMMP_MAX_K) kc = MMMP_MAX_K;
 
     mmmp_pool_keep();
@@ -114,7 +126,7 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
     int rc = MMMP_OK;
     int64_t n_nodes = 0;
     {
-        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, edges, ecoll;
+        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, edges, ecoll, amb;
         const int L = nj + 1;
         auto T = [&](cudaError_t e) {
             if (e != cudaSuccess && rc == MMMP_OK) rc = MMMP_ERR_CUDA_BASE + (int)e;
@@ -143,8 +155,10 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
             const int64_t n = n_nodes;
             T(nq64.alloc(sizeof(double) * n * D));
             T(nq32.alloc(sizeof(float) * n * ld32));
-            T(cidx.alloc(sizeof(int32_t) * n * kc));
-            T(cdist.alloc(sizeof(float) * n * kc));
+            const int kc_wide = k + 16 > MMMP_MAX_K ? MMMP_MAX_K : k + 16;
+            T(cidx.alloc(sizeof(int32_t) * n * kc_wide));
+            T(cdist.alloc(sizeof(float) * n * kc_wide));
+            T(amb.alloc(((n + 3) & ~(int64_t)3) + sizeof(int)));
             T(ridx.alloc(sizeof(int32_t) * n * k));
             T(rdist.alloc(sizeof(double) * n * k));
             T(edges.alloc(sizeof(int32_t) * n * k * 2));
@@ -201,12 +215,24 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                     filt_ptr = feat_ptr;
                     ldfilt = ldf;
                 }
-                R(mmmp_knn(filt_ptr, feat_ptr, n, filt_ptr, feat_ptr, n, ldfilt, ldfilt == 4 && filt_ptr != feat_ptr ? 3 : m32.dim,
-                           ldf, &m32, kc, 1, 0, 0,
-                           cidx.as<int32_t>(), cdist.as<float>(), s));
-                cudaEventRecord(ev[4], s);
-                R(mmmp_knn_refine(ref64_ptr, ref64_ptr, ld64, &m64, cidx.as<int32_t>(), cdist.as<float>(), n, kc, k,
-                                  1e-6, ridx.as<int32_t>(), rdist.as<double>(), nullptr, s));
+                int* any_amb = reinterpret_cast<int*>(amb.as<uint8_t>() + ((n + 3) & ~(int64_t)3));
+                for (int attempt = 0; attempt < 2 && rc == MMMP_OK; ++attempt) {
+                    R(mmmp_knn(filt_ptr, feat_ptr, n, filt_ptr, feat_ptr, n, ldfilt,
+                               ldfilt == 4 && filt_ptr != feat_ptr ? 3 : m32.dim, ldf, &m32, kc, 1, 0, 0,
+                               cidx.as<int32_t>(), cdist.as<float>(), s));
+                    if (attempt == 0) cudaEventRecord(ev[4], s);
+                    R(mmmp_knn_refine(ref64_ptr, ref64_ptr, ld64, &m64, cidx.as<int32_t>(), cdist.as<float>(), n, kc, k,
+                                      1e-6, ridx.as<int32_t>(), rdist.as<double>(), amb.as<uint8_t>(), s));
+                    if (kc >= kc_wide) break;
+                    int flagged = 0;
+                    T(cudaMemsetAsync(any_amb, 0, sizeof(int), s));
+                    int g = mmmp_div_up(n, 256);
+                    MMMP_LAUNCH(any_flag_kernel, g > 148 * 8 ? 148 * 8 : g, 256, 0, s, amb.as<uint8_t>(), n, any_amb);
+                    T(cudaMemcpyAsync(&flagged, any_amb, sizeof(int), cudaMemcpyDeviceToHost, s));
+                    T(cudaStreamSynchronize(s));
+                    if (!flagged) break;
+                    kc = kc_wide;
+                }
                 cudaEventRecord(ev[5], s);
                 R(mmmp_edges_from_knn(ridx.as<int32_t>(), n, k, edges.as<int32_t>(), s));
                 R(mmmp_collide_edges(w, robot, nq32.p, ld32, edges.as<int32_t>(), n * k, n_steps, step, flags,

@@ -883,6 +883,7 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         // grid resolution: ~16 rows per cell, 1..7 bits per axis
         int bits = 1;
         while (bits < 7 && ((int64_t)1 << (3 * (bits + 1))) * 16 <= n_ref) ++bits;
+        if (const char* e = getenv("MMMP_KNN_BITS")) bits = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
         KNN_TRY(cudaMallocAsync(&bbox, 6 * sizeof(int), s));
         const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
         KNN_TRY(cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, s));

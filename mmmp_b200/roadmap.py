@@ -72,7 +72,7 @@ def all_gather_rows(t: torch.Tensor, size: int, group=None) -> torch.Tensor:
 class RoadmapBuilder:
     def __init__(self, world: core.SpatialWorld, robot: int = 0, metric: str = "fk", k: int = 10,
                  n_steps: int = 50, step: float = 0.02, flags: int = CHECK_SELF | CHECK_OBSTACLES,
-                 group=None, timer: Optional[PhaseTimer] = None, knn_pad: int = 6, single_rank: bool = False):
+                 group=None, timer: Optional[PhaseTimer] = None, knn_pad: int = 2, single_rank: bool = False):
         self.world, self.robot, self.metric, self.k = world, robot, metric, k
         self.n_steps, self.step, self.flags, self.knn_pad = n_steps, step, flags, knn_pad
         self.group = group
@@ -140,10 +140,16 @@ class RoadmapBuilder:
         feats = self.features(q64, q32)
         mine = feats.rows(lo, hi)
         self._mark("features")
+        # the fp32 scan keeps k + knn_pad candidates for the fp64 re-rank; rows the re-rank cannot
+        # separate from the last candidate (`ambiguous`, ~1e-8 per query at pad 2) trigger one
+        # repeat of the scan with k + 16 candidates
         kc = min(self.k + self.knn_pad, 64)
         ci, cd = core.knn(feats, mine, kc, exclude_self=True, causal=False, query_id0=lo)
         self._mark("knn_scan")
         idx, dist, amb = core.knn_refine(feats.x64, mine.x64, feats.m64, ci, cd, self.k)
+        if kc < min(self.k + 16, 64) and bool(amb.any()):
+            ci, cd = core.knn(feats, mine, min(self.k + 16, 64), exclude_self=True, causal=False, query_id0=lo)
+            idx, dist, amb = core.knn_refine(feats.x64, mine.x64, feats.m64, ci, cd, self.k)
         self._mark("knn_rerank")
         edges = core.edges_from_knn(idx)
         if lo > 0:
