@@ -269,6 +269,19 @@ int mmmp_knn(const float* fref_d, const float* xref_d, int64_t n_ref,
              int exclude_self, int causal, int64_t query_id0, int32_t* out_idx_d,
              float* out_dist_d, void* stream);
 
+/* Multi-GPU form of mmmp_knn for a search of a set against itself:
+ * the library orders the rows spatially before it scans them, and rank `shard`
+ * of `n_shards` answers one contiguous slice of THAT order -- compact query
+ * blocks, the same tile culling as on one GPU, 1/n_shards of the work -- instead
+ * of a slice of the caller's row order.  out_rows_d [cap] receives the original
+ * row of every answered query, out_idx_d / out_dist_d [cap, k] its neighbours,
+ * *n_rows_h (host) their number; cap >= (ceil(ceil(n/128) / n_shards) + 1) * 128.
+ * The union over the shards is every row exactly once.                      */
+int mmmp_knn_shard(const float* fref_d, const float* xref_d, int64_t n_ref, int ldf, int fdim,
+                   int ldx, const mmmp_metric* metric, int k, int exclude_self, int shard,
+                   int n_shards, int32_t* out_rows_d, int64_t* n_rows_h, int32_t* out_idx_d,
+                   float* out_dist_d, void* stream);
+
 /* profiling aid: enable != 0 turns on five device counters of the scan kernel
  * (exact evaluations, list insertions, warp drains, tiles loaded, most tiles
  * loaded by one CTA); out5_h (may be NULL) receives and resets them;

@@ -320,6 +320,23 @@ def knn(ref: Features, query: Features, k: int, exclude_self: bool = True, causa
     return idx, dist
 
 
+def knn_shard(ref: Features, k: int, shard: int, n_shards: int, exclude_self: bool = True):
+    """The slice `shard` of `n_shards` of a search of `ref` against itself, cut in the library's
+    spatial scan order (mmmp_knn_shard) -> (rows [m] int32: original row of every answered query,
+    idx [m, k] int32, dist [m, k] fp32).  The shards together answer every row exactly once."""
+    fr, xr = _dev(ref.filt, torch.float32), _dev(ref.x32, torch.float32)
+    n = fr.shape[0]
+    cap = (-(-(-(-n // 128)) // n_shards) + 1) * 128
+    rows = torch.empty((cap,), dtype=torch.int32, device=fr.device)
+    idx = torch.empty((cap, k), dtype=torch.int32, device=fr.device)
+    dist = torch.empty((cap, k), dtype=torch.float32, device=fr.device)
+    m = C.c_int64(0)
+    fdim = ref.fdim or ref.m32.dim
+    _lib.call("mmmp_knn_shard", _ptr(fr), _ptr(xr), n, fr.shape[1], fdim, xr.shape[1], C.byref(ref.m32), k,
+              int(exclude_self), shard, n_shards, _ptr(rows), C.byref(m), _ptr(idx), _ptr(dist), _stream())
+    return rows[:m.value], idx[:m.value], dist[:m.value]
+
+
 def knn_refine(ref64: torch.Tensor, query64: torch.Tensor, metric64: Metric, cand_idx: torch.Tensor,
                cand_dist: torch.Tensor, k: int, tie_eps: float = 1e-6):
     """fp64 re-rank -> (idx [nq, k], dist64 [nq, k], ambiguous [nq] u8)."""

@@ -178,6 +178,27 @@ cell_scatter_kernel(const uint32_t* __restrict__ keys, int64_t n, const int64_t*
     }
 }
 
+// The scatter above leaves the rows of a cell in the order their atomics landed.  One warp per
+// cell puts them in ascending row order (rank by counting), so that the scan order is a pure
+// function of the data: the shards of a multi-GPU search (mmmp_knn_shard) then cut the SAME
+// order on every rank, and a search repeats bit for bit.
+__global__ void __launch_bounds__(256)
+cell_order_kernel(const int32_t* __restrict__ in, const int64_t* __restrict__ offsets, int n_cells,
+                  int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_cells;
+         c += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t o0 = offsets[c];
+        const int m = (int)(offsets[c + 1] - o0);
+        for (int i = lane; i < m; i += 32) {
+            const int32_t v = in[o0 + i];
+            int rank = 0;
+            for (int j = 0; j < m; ++j) rank += in[o0 + j] < v;
+            out[o0 + rank] = v;
+        }
+    }
+}
+
 // ---- row packing ----------------------------------------------------------------------
 // filter rows: out[p] = [in[perm[p]][0..d), 0 .., (1 - eps) * |.|^2]   (W columns); perm may be NULL
 __global__ void __launch_bounds__(256)
@@ -252,6 +273,9 @@ struct KnnArgs {
     int ldx, S, kc;
     int flags;             // 1 = exclude self, 2 = causal, 4 = queries ARE the references (same scan order)
     int tiles_per_split, n_splits;
+    int qblock0;           // first query block (of LS scan positions) this launch covers
+    int32_t* out_rows;     // sharded launch: compact output, row r = scan position qblock0 * LS + r;
+                           // out_rows[r] = original query row (NULL: output indexed by original row)
     int32_t* out_idx;      // [n_query, n_splits, kc]
     float* out_val;        // candidate-list domain (L2/SQ_SUM: squared ; GROUP: distance)
     unsigned long long* stats;  // optional: [0] exact evaluations, [1] insertions, [2] drains, [3] tiles loaded, [4] most tiles loaded by one CTA
@@ -337,7 +361,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     }
 
     // ---- reference tiles of this CTA ---------------------------------------------
-    const int64_t q_first = (int64_t)blockIdx.x * LS;
+    const int64_t q_first = ((int64_t)blockIdx.x + A.qblock0) * LS;
     int64_t ref_end = A.n_ref;
     if (A.flags & 2) {
         const int64_t last_q = A.query_id0 + q_first + LS;  // exclusive bound on this CTA's query ids
@@ -678,7 +702,12 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
         const int64_t qi = q_first + qq * KNN_CTHREADS + tid;
         if (qi >= A.n_query) continue;
         const int col = qq * KNN_CTHREADS + tid;
-        const size_t o = ((size_t)qrow[qq] * A.n_splits + blockIdx.y) * kc;
+        size_t o = ((size_t)qrow[qq] * A.n_splits + blockIdx.y) * kc;
+        if (A.out_rows) {
+            const int64_t r = qi - (int64_t)A.qblock0 * LS;
+            o = ((size_t)r * A.n_splits + blockIdx.y) * kc;
+            if (blockIdx.y == 0) A.out_rows[r] = (int32_t)qrow[qq];
+        }
         for (int c = 0; c < kc; ++c) {
             const int id = li[c * LS + col];
             A.out_idx[o + c] = id == 0x7fffffff ? -1 : id;
@@ -780,8 +809,18 @@ int spatial_perm(const float* rows, int ld, int nd, int64_t n, const int* bbox_d
     MMMP_LAUNCH(cell_hist_kernel, grid_for(n, sms), 256, 0, stream, rows, ld, nd, n, bbox_d, bits, keys, hist);
     int rc = mmmp_exclusive_scan_i32(hist, n_cells, offs, stream);
     if (rc == MMMP_OK) {
-        MMMP_LAUNCH(cell_scatter_kernel, grid_for(n, sms), 256, 0, stream, keys, n, offs, hist + n_cells, perm);
-        cudaError_t e = cudaPeekAtLastError();
+        int32_t* unordered = reinterpret_cast<int32_t*>(keys);  // the keys are dead once scattered ...
+        int32_t* scratch = nullptr;                             // ... but are read while it runs
+        cudaError_t e = cudaMallocAsync(&scratch, sizeof(int32_t) * n, s);
+        if (e == cudaSuccess) {
+            unordered = scratch;
+            MMMP_LAUNCH(cell_scatter_kernel, grid_for(n, sms), 256, 0, stream, keys, n, offs, hist + n_cells, unordered);
+            int g = mmmp_div_up((int64_t)n_cells * 32, 256);
+            if (g > sms * 32) g = sms * 32;
+            MMMP_LAUNCH(cell_order_kernel, g, 256, 0, stream, unordered, offs, n_cells, perm);
+            e = cudaPeekAtLastError();
+            cudaFreeAsync(scratch, s);
+        }
         if (e != cudaSuccess) rc = MMMP_ERR_CUDA_BASE + (int)e;
     }
     cudaFreeAsync(keys, s);
@@ -810,10 +849,13 @@ extern "C" int mmmp_knn_stats(int enable, unsigned long long* out5_h) {
     return MMMP_OK;
 }
 
-extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, const float* fquery,
-                        const float* xquery, int64_t n_query, int ldf, int fdim, int ldx, const mmmp_metric* metric,
-                        int k, int exclude_self, int causal, int64_t query_id0, int32_t* out_idx, float* out_dist,
-                        void* stream) {
+// shard >= 0: the queries are the references and only the query blocks of shard `shard` of
+// `n_shards` (contiguous in scan order) are searched; output rows are compact (out_rows names
+// the original row of each) and *n_rows_h receives their number
+static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const float* fquery, const float* xquery,
+                    int64_t n_query, int ldf, int fdim, int ldx, const mmmp_metric* metric, int k, int exclude_self,
+                    int causal, int64_t query_id0, int shard, int n_shards, int32_t* out_rows, int64_t* n_rows_h,
+                    int32_t* out_idx, float* out_dist, void* stream) {
     if (!fref || !xref || !fquery || !xquery || !out_idx || n_ref < 0 || n_query < 0 || k < 1 || k > MMMP_MAX_K)
         return MMMP_ERR_ARG;
     if (n_ref >= (1ll << 28)) return MMMP_ERR_LIMIT;
@@ -834,7 +876,7 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     // queries per thread: measured on B200 (1M x 1M, FK and joint-space metrics), one query per
     // thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM
-    const int qmax = F4 <= 2 ? 2 : 1;
+    const int qmax = (F4 <= 2 && shard < 0) ? 2 : 1;
     int Q = 1;
     if (const char* e = getenv("MMMP_KNN_Q")) {
         const int q = atoi(e);
@@ -844,7 +886,18 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     if (scan_smem(F4, Q, k, S) > (size_t)max_smem) return MMMP_ERR_LIMIT;
     bool cull = !causal && n_ref >= KNN_CULL_MIN;
     if (const char* e = getenv("MMMP_KNN_CULL")) cull = cull && atoi(e) != 0;
-    const int n_qblocks = mmmp_div_up(n_query, (int64_t)KNN_CTHREADS * Q);
+    const int all_qblocks = mmmp_div_up(n_query, (int64_t)KNN_CTHREADS * Q);
+    int qblock0 = 0, n_qblocks = all_qblocks;
+    int64_t n_rows = n_query;  // rows this launch answers
+    if (shard >= 0) {
+        qblock0 = (int)((int64_t)all_qblocks * shard / n_shards);
+        n_qblocks = (int)((int64_t)all_qblocks * (shard + 1) / n_shards) - qblock0;
+        const int64_t first = (int64_t)qblock0 * KNN_CTHREADS * Q, end = ((int64_t)qblock0 + n_qblocks) * KNN_CTHREADS * Q;
+        n_rows = (end < n_query ? end : n_query) - first;
+        if (n_rows < 0) n_rows = 0;
+        if (n_rows_h) *n_rows_h = n_rows;
+        if (n_rows == 0) return MMMP_OK;
+    }
     const int64_t total_tiles = (n_ref + KNN_TILE - 1) / KNN_TILE;
     int n_splits = 1;
     if (!cull && n_qblocks < 2 * sms) {
@@ -859,7 +912,7 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     int* bbox = nullptr;
     float* tmp_val = nullptr;
     const int nd = fdim < 3 ? fdim : 3;
-    const size_t n_out = (size_t)n_query * n_splits * k;
+    const size_t n_out = (size_t)n_rows * n_splits * k;
     const int64_t n_ref4 = (n_ref + 3) & ~(int64_t)3;
     auto cleanup = [&]() {
         void* ptrs[] = {pref, same ? nullptr : pquery, boxes, xs, perm, same ? nullptr : qperm, bbox, tmp_idx, tmp_val};
@@ -928,6 +981,8 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     A.kc = k;
     A.flags = (exclude_self ? 1 : 0) | (causal ? 2 : 0) | ((same && query_id0 == 0) ? 4 : 0);
     A.n_splits = n_splits;
+    A.qblock0 = qblock0;
+    A.out_rows = shard >= 0 ? out_rows : nullptr;
     A.tiles_per_split = (int)((total_tiles + n_splits - 1) / n_splits);
     if (A.tiles_per_split < 1) A.tiles_per_split = 1;
     A.stats = g_knn_stats;
@@ -943,9 +998,9 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
         default: rc = MMMP_ERR_LIMIT;
     }
     if (rc == MMMP_OK) {
-        int g = mmmp_div_up(n_query, 128);
+        int g = mmmp_div_up(n_rows, 128);
         if (g > sms * 8) g = sms * 8;
-        MMMP_LAUNCH(knn_merge_kernel, g, 128, 0, stream, tmp_idx, tmp_val, n_query, n_splits, k, A.M.kind, out_idx,
+        MMMP_LAUNCH(knn_merge_kernel, g, 128, 0, stream, tmp_idx, tmp_val, n_rows, n_splits, k, A.M.kind, out_idx,
                     out_dist);
         cudaError_t e = cudaPeekAtLastError();
         if (e != cudaSuccess) rc = MMMP_ERR_CUDA_BASE + (int)e;
@@ -953,4 +1008,20 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
     cleanup();
 #undef KNN_TRY
     return rc;
+}
+
+extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, const float* fquery,
+                        const float* xquery, int64_t n_query, int ldf, int fdim, int ldx, const mmmp_metric* metric,
+                        int k, int exclude_self, int causal, int64_t query_id0, int32_t* out_idx, float* out_dist,
+                        void* stream) {
+    return knn_impl(fref, xref, n_ref, fquery, xquery, n_query, ldf, fdim, ldx, metric, k, exclude_self, causal,
+                    query_id0, -1, 1, nullptr, nullptr, out_idx, out_dist, stream);
+}
+
+extern "C" int mmmp_knn_shard(const float* fref, const float* xref, int64_t n_ref, int ldf, int fdim, int ldx,
+                              const mmmp_metric* metric, int k, int exclude_self, int shard, int n_shards,
+                              int32_t* out_rows, int64_t* n_rows_h, int32_t* out_idx, float* out_dist, void* stream) {
+    if (shard < 0 || n_shards < 1 || shard >= n_shards || !out_rows || !n_rows_h) return MMMP_ERR_ARG;
+    return knn_impl(fref, xref, n_ref, fref, xref, n_ref, ldf, fdim, ldx, metric, k, exclude_self, 0, 0, shard,
+                    n_shards, out_rows, n_rows_h, out_idx, out_dist, stream);
 }

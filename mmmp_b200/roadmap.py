@@ -69,6 +69,23 @@ def all_gather_rows(t: torch.Tensor, size: int, group=None) -> torch.Tensor:
     return torch.cat([outs[g][: ns[g]] for g in range(size)], 0)
 
 
+def all_gather_padded(t: torch.Tensor, cap: int, size: int, group=None, fill=0) -> torch.Tensor:
+    """Every rank contributes at most `cap` rows; -> [size * cap, ...] with rank g's rows at
+    [g * cap, g * cap + its row count) and `fill` in the padding.  One collective, no size
+    exchange, no host synchronisation."""
+    import torch.distributed as dist
+    pad = torch.full((cap,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = torch.empty((size * cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    try:
+        dist.all_gather_into_tensor(out, pad, group=group)
+    except (RuntimeError, NotImplementedError):      # backends without the flat form
+        parts = [torch.empty_like(pad) for _ in range(size)]
+        dist.all_gather(parts, pad, group=group)
+        out = torch.cat(parts, 0)
+    return out
+
+
 class RoadmapBuilder:
     def __init__(self, world: core.SpatialWorld, robot: int = 0, metric: str = "fk", k: int = 10,
                  n_steps: int = 50, step: float = 0.02, flags: int = CHECK_SELF | CHECK_OBSTACLES,
@@ -134,33 +151,64 @@ class RoadmapBuilder:
 
     def candidates(self, q64: torch.Tensor, q32: torch.Tensor, gather: bool = True):
         """k nearest candidates of every node + the verdict of every candidate edge.
-        -> dict(idx [n,k] int32, dist [n,k] fp64, edge_free [n,k] uint8, ambiguous [n] uint8)"""
+        -> dict(idx [n,k] int32, dist [n,k] fp64, edge_free [n,k] uint8, ambiguous [n] uint8).
+        With several ranks:
+          * neighbour search -- every rank answers one slice of the library's SPATIAL scan order
+            (core.knn_shard): its query blocks stay as compact as on one GPU, the tile culling
+            keeps its selectivity and a rank does 1/size of the work; the answered rows are
+            all-gathered and scattered back to the caller's row order;
+          * edge checks -- every rank takes a contiguous block of the caller's rows (the sampling
+            order: hard and easy edges mixed, so the ranks finish together), verdicts all-gathered.
+        gather=False returns this rank's row block [lo, hi) of every table ("rows")."""
         n = q64.shape[0]
         lo, hi = shard_rows(n, self.rank, self.size)
         feats = self.features(q64, q32)
-        mine = feats.rows(lo, hi)
         self._mark("features")
         # the fp32 scan keeps k + knn_pad candidates for the fp64 re-rank; rows the re-rank cannot
         # separate from the last candidate (`ambiguous`, ~1e-8 per query at pad 2) trigger one
         # repeat of the scan with k + 16 candidates
-        kc = min(self.k + self.knn_pad, 64)
-        ci, cd = core.knn(feats, mine, kc, exclude_self=True, causal=False, query_id0=lo)
+        kc, kc_wide = min(self.k + self.knn_pad, 64), min(self.k + 16, 64)
+
+        def scan(kc_):
+            if self.size == 1:
+                ci, cd = core.knn(feats, feats, kc_, exclude_self=True, causal=False)
+                return None, ci, cd, feats.x64
+            r, ci, cd = core.knn_shard(feats, kc_, self.rank, self.size, exclude_self=True)
+            return r, ci, cd, core.gather_rows(feats.x64, r)
+
+        rows, ci, cd, mine64 = scan(kc)
         self._mark("knn_scan")
-        idx, dist, amb = core.knn_refine(feats.x64, mine.x64, feats.m64, ci, cd, self.k)
-        if kc < min(self.k + 16, 64) and bool(amb.any()):
-            ci, cd = core.knn(feats, mine, min(self.k + 16, 64), exclude_self=True, causal=False, query_id0=lo)
-            idx, dist, amb = core.knn_refine(feats.x64, mine.x64, feats.m64, ci, cd, self.k)
+        idx, dist, amb = core.knn_refine(feats.x64, mine64, feats.m64, ci, cd, self.k)
+        if kc < kc_wide and bool(amb.any()):
+            rows, ci, cd, mine64 = scan(kc_wide)
+            idx, dist, amb = core.knn_refine(feats.x64, mine64, feats.m64, ci, cd, self.k)
         self._mark("knn_rerank")
-        edges = core.edges_from_knn(idx)
+        if rows is not None:   # spatial slices -> the caller's row order, on every rank
+            cap = (-(-(-(-n // 128)) // self.size) + 1) * 128          # rows a shard can hold (core.knn_shard)
+            at = all_gather_padded(rows, cap, self.size, self.group, fill=n).long()   # padding -> row n
+            tables = []
+            for part in (idx, dist, amb):
+                part = all_gather_padded(part, cap, self.size, self.group)
+                full = torch.empty((n + 1,) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+                full[at] = part
+                tables.append(full[:n])
+            idx, dist, amb = tables
+            self._mark("gather_adjacency")
+        mine = idx[lo:hi].contiguous() if self.size > 1 else idx
+        edges = core.edges_from_knn(mine)
         if lo > 0:
             edges[:, 0] += lo
         hit = self.world.collide_edges(q32, edges, self.n_steps, self.step, self.robot, self.flags)
         free = (hit == 0).to(torch.uint8).reshape(hi - lo, self.k)
         self._mark("edge_collision")
-        if gather and self.size > 1:
-            idx, dist, free, amb = (self._all_gather_rows(t) for t in (idx, dist, free, amb))
-            self._mark("gather_adjacency")
-        return {"idx": idx, "dist": dist, "edge_free": free, "ambiguous": amb, "rows": (lo, hi)}
+        if self.size > 1:
+            if gather:   # equal row blocks (the last may be short): rank order = row order
+                per = (n + self.size - 1) // self.size
+                free = all_gather_padded(free, per, self.size, self.group)[:n]
+                self._mark("gather_adjacency")
+            else:
+                idx, dist, amb = idx[lo:hi], dist[lo:hi], amb[lo:hi]
+        return {"idx": idx, "dist": dist, "edge_free": free, "ambiguous": amb, "rows": (lo, hi) if not gather else (0, n)}
 
     def build(self, n: int, seed: int):
         q64, q32 = self.sample_free(n, seed)

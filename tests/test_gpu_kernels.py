@@ -354,6 +354,27 @@ def test_knn_large_vs_float64_bruteforce(core, cuda, D, n, k):
     assert amb.mean() < 0.05
 
 
+def test_knn_shards_tile_the_unsharded_search(core, panda_model, cuda):
+    """mmmp_knn_shard: the shards of a self-search answer every row exactly once and every answer
+    is bit-identical to the unsharded search (culled path at 40 000 rows, exhaustive path at
+    3 000, FK metric and L2, shard counts that do not divide the block count)."""
+    rng = np.random.default_rng(91)
+    w = core.SpatialWorld([core.RobotSpec(panda_model, core.base_matrix((0, 0, 0.01)))], [])
+    for n in (3000, 40000):
+        q = np.round(rng.uniform(LIMITS[:, 0], LIMITS[:, 1], (n, 7)), 2)
+        q64 = core.to_device_f64(q)
+        q32 = core.pack_f32(q64)
+        for F in (w.fk_features(q64, q32, 0), core.l2_features(q64, q32)):
+            ref_i, ref_d = core.knn(F, F, 12, exclude_self=True)
+            for shards in (1, 3, 8):
+                seen = torch.zeros(n, dtype=torch.int32, device=cuda)
+                for s in range(shards):
+                    rows, idx, dist = core.knn_shard(F, 12, s, shards)
+                    seen[rows.long()] += 1
+                    assert (idx == ref_i[rows.long()]).all() and (dist == ref_d[rows.long()]).all()
+                assert (seen == 1).all()
+
+
 def test_knn_causal_and_queries_subset(core, cuda):
     rng = np.random.default_rng(5)
     q = np.round(rng.uniform(-3, 3, (4000, 4)), 2)

@@ -41,6 +41,27 @@ def _worker(rank, size, port, out):
             lo, hi = shard_rows(n, rank, size)
             blocks = all_gather_rows(torch.arange(lo, hi)[:, None], size)
             ok &= bool((blocks[:, 0] == torch.arange(n)).all())
+        # spatial shards: every rank answers an arbitrary subset of the rows (mmmp_knn_shard);
+        # gather of (row ids, values) + scatter restores the caller's row order
+        n = 1003
+        perm = torch.from_numpy(np.random.default_rng(5).permutation(n))
+        lo, hi = shard_rows(n, rank, size)
+        rows = perm[lo:hi]
+        vals = (rows * 10).to(torch.float64)[:, None].repeat(1, 2)
+        at = all_gather_rows(rows, size).long()
+        part = all_gather_rows(vals, size)
+        full = torch.empty((n, 2), dtype=part.dtype)
+        full[at] = part
+        ok &= bool((full[:, 0] == torch.arange(n) * 10).all())
+        # the same through the padded single-collective form RoadmapBuilder.candidates uses:
+        # padding rows carry the sentinel id n and land in a spare row
+        from mmmp_b200.roadmap import all_gather_padded
+        cap = (n + size - 1) // size + 7
+        at = all_gather_padded(rows, cap, size, fill=n).long()
+        part = all_gather_padded(vals, cap, size)
+        full = torch.empty((n + 1, 2), dtype=part.dtype)
+        full[at] = part
+        ok &= bool((full[:n, 0] == torch.arange(n) * 10).all()) and at.shape[0] == size * cap
         # sampling blocks: rank r draws candidates [first + r*per, first + (r+1)*per); the rank-ordered
         # concatenation equals the single-rank stream (counter-based generator)
         lo_, hi_ = np.array([-2.0, 0.0, -1.0]), np.array([2.0, 3.0, 1.0])
