@@ -15,6 +15,8 @@
  *     passed as void*, NULL = legacy default stream); the caller owns and
  *     allocates every output buffer; nothing is retained after return;
  *   - return value: 0 = MMMP_OK, 1..99 = argument error, 1000+e = cudaError e;
+ *   - a call with a row count of 0 returns MMMP_OK without touching its buffers, but
+ *     required pointers must still be non-NULL (NULL always means "argument missing");
  *   - configurations are row-major [N, ld] with ld >= D; the fp32 copies used
  *     by the spatial kernels are padded to ld % 4 == 0 for 16-byte loads.
  *   - there is NO CPU fallback: without a CUDA device every compute entry

@@ -181,8 +181,20 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_EMPTY = {}   # device -> a 16-byte buffer whose address stands in for empty tensors
+
+
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
-    return C.c_void_p(0 if t is None else t.data_ptr())
+    """Device address of a tensor; NULL only for None.  torch gives empty tensors a NULL
+    data_ptr, which the C ABI would take for a missing argument, so they get the address of a
+    small live buffer instead (never dereferenced: their row count is 0)."""
+    if t is None:
+        return C.c_void_p(0)
+    if t.numel() == 0 and t.is_cuda:
+        if t.device not in _EMPTY:
+            _EMPTY[t.device] = torch.zeros(16, dtype=torch.uint8, device=t.device)
+        return C.c_void_p(_EMPTY[t.device].data_ptr())
+    return C.c_void_p(t.data_ptr())
 
 
 def _require_cuda() -> torch.device:

@@ -375,6 +375,44 @@ def test_knn_shards_tile_the_unsharded_search(core, panda_model, cuda):
                 assert (seen == 1).all()
 
 
+def test_empty_and_tiny_inputs(core, panda_model, cuda):
+    """Edge cases of every entry point: zero rows, one row, fewer references than k (missing
+    neighbours are -1 / inf, as the reference's heap simply holds fewer entries), ragged sizes."""
+    from mmmp_b200._lib import CHECK_OBSTACLES, CHECK_SELF
+    w = core.SpatialWorld([core.RobotSpec(panda_model, core.base_matrix((0, 0, 0.01)))], [core.plane((0, 0, 1), 0.0)])
+    F = CHECK_SELF | CHECK_OBSTACLES
+    empty64 = torch.empty((0, 7), dtype=torch.float64, device=cuda)
+    empty32 = core.pack_f32(empty64)
+    assert empty32.shape == (0, 8)
+    assert w.collide_configs(empty32, 0, F).shape == (0,)
+    assert core.compact_free(torch.empty((0,), dtype=torch.uint8, device=cuda)).shape == (0,)
+    e = torch.empty((0, 2), dtype=torch.int32, device=cuda)
+    q = np.round(np.random.default_rng(3).uniform(LIMITS[:, 0], LIMITS[:, 1], (5, 7)), 2)
+    q64 = core.to_device_f64(q)
+    q32 = core.pack_f32(q64)
+    assert w.collide_edges(q32, e, 50, 0.02, 0, F).shape == (0,)
+    labels, count = core.connected_components(torch.empty((0, 3), dtype=torch.int32, device=cuda))
+    assert labels.shape == (0,) and count == 0
+    # 5 references, k = 10: every row has its 4 neighbours, then -1 / inf
+    feats = w.fk_features(q64, q32, 0)
+    idx, dist, amb = core.knn_exact(feats, feats, 10)
+    idx, dist = _np(idx), _np(dist)
+    assert (np.sort(idx[:, :4], 1) == np.array([[j for j in range(5) if j != i] for i in range(5)])).all()
+    assert (idx[:, 4:] == -1).all() and np.isinf(dist[:, 4:]).all() and np.isfinite(dist[:, :4]).all()
+    # a single row: no neighbour at all; its edge slots are reported blocked
+    one = w.fk_features(q64[:1].contiguous(), q32[:1].contiguous(), 0)
+    idx1, _, _ = core.knn_exact(one, one, 3)
+    assert (_np(idx1) == -1).all()
+    edges = core.edges_from_knn(idx1)
+    assert _np(w.collide_edges(q32[:1].contiguous(), edges, 50, 0.02, 0, F)).tolist() == [1, 1, 1]
+    # shards of a tiny set: still every row once
+    seen = torch.zeros(5, dtype=torch.int64, device=cuda)
+    for s in range(4):
+        rows, _, _ = core.knn_shard(feats, 3, s, 4)
+        seen += torch.bincount(rows.long(), minlength=5)
+    assert (seen == 1).all()
+
+
 def test_knn_causal_and_queries_subset(core, cuda):
     rng = np.random.default_rng(5)
     q = np.round(rng.uniform(-3, 3, (4000, 4)), 2)
