@@ -1,15 +1,11 @@
-// Kernel (d): brute-force k-NN and radius neighbour search.
+// Kernel (d), second half: fp64 re-rank of the scan's candidates and the radius search
+// (the fp32 scan itself lives in knn_scan.cu).
 //
-// Scan kernel (fp32, CUDA cores): every thread owns Q queries in registers;
-// reference rows stream HBM/L2 -> shared memory in 16-byte-aligned tiles moved
-// by the TMA engine (cp.async.bulk + mbarrier, 3 stages); the hot loop is a
-// weighted dot-product filter  B_r - 2<a,r> <= tau - A_q  (dim FFMAs + 1 compare
-// per pair, a conservative lower bound of the metric) and only the rare
-// survivors evaluate the metric exactly and are inserted into the thread's
-// sorted candidate column in shared memory.
 // Re-rank kernel (fp64): the kc >= k candidates are re-evaluated in fp64 in the
 // reference's arithmetic order and sorted by (distance, id) so that the result
 // equals the reference's float64 ranking wherever fp32 could separate ranks.
+// Radius kernel: fp32 lower-bound filter per (query, reference) pair, exact fp64 metric on
+// the survivors, two passes (count, then fill a CSR table).
 //
 // Reference call sites replaced: heap loops decoupled_prm.py:480-504,527-550,
 // 553-571,943-995; KDTree.query / query_ball_point coupled/degree_coupled_prm.py:67,82,
@@ -22,7 +18,6 @@
 namespace {
 
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_STAGES = 3;
 constexpr int KNN_TILE = 128;          // reference rows per shared-memory tile
 constexpr float KNN_SLACK = 2.0e-5f;   // relative slack of the fp32 filter
 
@@ -31,277 +26,12 @@ struct MetricDev {
     float w[MMMP_MAX_GROUPS];
 };
 
-// ---- mbarrier / TMA bulk copy (sm_90+; sm_100a here) -----------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// exact fp32 metric between a register query and a shared-memory row, in the
-// candidate list's domain: L2 / SQ_SUM -> squared distance ; GROUP -> distance
-template <int F4>
-__device__ __forceinline__ float exact_metric_f32(const MetricDev& M, const float* a, const float4* row) {
-    float d[F4 * 4];
-#pragma unroll
-    for (int i = 0; i < F4; ++i) {
-        const float4 r = row[i];
-        d[4 * i + 0] = a[4 * i + 0] - r.x;
-        d[4 * i + 1] = a[4 * i + 1] - r.y;
-        d[4 * i + 2] = a[4 * i + 2] - r.z;
-        d[4 * i + 3] = a[4 * i + 3] - r.w;
-    }
-    if (M.kind == MMMP_METRIC_GROUP_L2_SUM) {
-        float s = 0.f;
-#pragma unroll
-        for (int g = 0; g < (F4 * 4) / 3; ++g)
-            if (g < M.n_groups) {
-                const float n2 = fmaf(d[3 * g], d[3 * g], fmaf(d[3 * g + 1], d[3 * g + 1], d[3 * g + 2] * d[3 * g + 2]));
-                s = fmaf(M.w[g], sqrtf(n2), s);
-            }
-        return s;
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < F4 * 4; ++i) s = fmaf(d[i], d[i], s);
-    return s;
-}
-
-// per-column weight of the filter's quadratic form
+// per-column weight of the radius filter's quadratic form
 __device__ __forceinline__ float filter_w2(const MetricDev& M, int col) {
     if (M.kind != MMMP_METRIC_GROUP_L2_SUM) return col < M.dim ? 1.f : 0.f;
     const int g = col / 3;
     return g < M.n_groups ? M.w[g] * M.w[g] : 0.f;
 }
-
-#if 0  // superseded by knn_scan.cu
-struct KnnArgs {
-    const float* ref;
-    const float* query;
-    int64_t n_ref, n_query, query_id0;
-    int ldf, kc, exclude_self, causal;
-    int tiles_per_split, n_splits;
-    int32_t* out_idx;   // [n_query, n_splits, kc]
-    float* out_val;     // list-domain values
-    MetricDev M;
-};
-
-template <int F4, int Q>
-__global__ void __launch_bounds__(KNN_THREADS)
-knn_scan_kernel(KnnArgs A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int ROWF = F4 * 4;
-    // layout: tiles[STAGES][TILE][ldf] | sB[STAGES][TILE] | lv[kc][T*Q] | li[kc][T*Q] | bars
-    const int ldf = A.ldf;
-    float* tiles = reinterpret_cast<float*>(smem_raw);
-    float* sB = tiles + (size_t)KNN_STAGES * KNN_TILE * ldf;
-    float* lv = sB + KNN_STAGES * KNN_TILE;
-    int* li = reinterpret_cast<int*>(lv + (size_t)A.kc * KNN_THREADS * Q);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)A.kc * KNN_THREADS * Q);
-
-    const int tid = threadIdx.x;
-    const int kc = A.kc;
-    const MetricDev& M = A.M;
-    constexpr int LS = KNN_THREADS * Q;  // list stride
-
-    // ---- queries into registers ------------------------------------------
-    const int64_t q_first = (int64_t)blockIdx.x * KNN_THREADS * Q;
-    float a[Q][ROWF], a2[Q][ROWF], thr[Q], Aq[Q], tau[Q];
-    int64_t qid[Q];
-    bool qvalid[Q];
-#pragma unroll
-    for (int qq = 0; qq < Q; ++qq) {
-        const int64_t qi = q_first + qq * KNN_THREADS + tid;
-        qvalid[qq] = qi < A.n_query;
-        qid[qq] = A.query_id0 + qi;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < ROWF; ++i) {
-            const float v = (qvalid[qq] && i < ldf) ? A.query[qi * ldf + i] : 0.f;
-            const float w2 = filter_w2(M, i);
-            a[qq][i] = v;
-            a2[qq][i] = -2.f * w2 * v;
-            acc = fmaf(w2 * v, v, acc);
-        }
-        Aq[qq] = acc * (1.f - KNN_SLACK);
-        tau[qq] = CUDART_INF_F;
-        thr[qq] = qvalid[qq] ? CUDART_INF_F : -CUDART_INF_F;
-        for (int c = 0; c < kc; ++c) {
-            lv[(size_t)c * LS + qq * KNN_THREADS + tid] = CUDART_INF_F;
-            li[(size_t)c * LS + qq * KNN_THREADS + tid] = -1;
-        }
-    }
-
-    // ---- reference range of this CTA ------------------------------------------
-    int64_t ref_end = A.n_ref;
-    if (A.causal) {
-        const int64_t last_q = A.query_id0 + q_first + (int64_t)KNN_THREADS * Q;  // exclusive bound on ids
-        if (last_q < ref_end) ref_end = last_q;
-    }
-    const int64_t total_tiles = (ref_end + KNN_TILE - 1) / KNN_TILE;
-    const int64_t tile_lo = (int64_t)blockIdx.y * A.tiles_per_split;
-    int64_t tile_hi = tile_lo + A.tiles_per_split;
-    if (tile_hi > total_tiles) tile_hi = total_tiles;
-    const int64_t n_tiles = tile_hi > tile_lo ? tile_hi - tile_lo : 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < KNN_STAGES; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int64_t t) {  // thread 0 only
-        const int s = (int)(t % KNN_STAGES);
-        const int64_t r0 = (tile_lo + t) * KNN_TILE;
-        int64_t cnt = ref_end - r0;
-        if (cnt > KNN_TILE) cnt = KNN_TILE;
-        const uint32_t bytes = (uint32_t)(cnt * ldf * sizeof(float));
-        mbar_expect_tx(&bars[s], bytes);
-        tma_load_1d(tiles + (size_t)s * KNN_TILE * ldf, A.ref + r0 * ldf, bytes, &bars[s]);
-    };
-    if (tid == 0)
-        for (int64_t t = 0; t < KNN_STAGES && t < n_tiles; ++t) issue(t);
-
-    for (int64_t t = 0; t < n_tiles; ++t) {
-        const int s = (int)(t % KNN_STAGES);
-        const uint32_t parity = (uint32_t)((t / KNN_STAGES) & 1);
-        const int64_t r0 = (tile_lo + t) * KNN_TILE;
-        int cnt = (int)((ref_end - r0) < KNN_TILE ? (ref_end - r0) : KNN_TILE);
-        mbar_wait(&bars[s], parity);
-        const float* tile = tiles + (size_t)s * KNN_TILE * ldf;
-        // B'_r of the filter for the rows of this tile
-        for (int j = tid; j < cnt; j += KNN_THREADS) {
-            const float* row = tile + (size_t)j * ldf;
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < ROWF; ++i) {
-                const float v = row[i];
-                acc = fmaf(filter_w2(M, i) * v, v, acc);
-            }
-            sB[s * KNN_TILE + j] = acc * (1.f - KNN_SLACK);
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int j = 0; j < cnt; ++j) {
-            const float4* row = reinterpret_cast<const float4*>(tile + (size_t)j * ldf);
-            float4 r[F4];
-#pragma unroll
-            for (int i = 0; i < F4; ++i) r[i] = row[i];
-            const float b = sB[s * KNN_TILE + j];
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq) {
-                float sacc = b;
-#pragma unroll
-                for (int i = 0; i < F4; ++i) {
-                    sacc = fmaf(a2[qq][4 * i + 0], r[i].x, sacc);
-                    sacc = fmaf(a2[qq][4 * i + 1], r[i].y, sacc);
-                    sacc = fmaf(a2[qq][4 * i + 2], r[i].z, sacc);
-                    sacc = fmaf(a2[qq][4 * i + 3], r[i].w, sacc);
-                }
-                if (sacc <= thr[qq]) {
-                    // ---- rare path: exact fp32 metric + sorted insert ----
-                    const int64_t id = r0 + j;
-                    bool ok = true;
-                    if (A.exclude_self && id == qid[qq]) ok = false;
-                    if (A.causal && id >= qid[qq]) ok = false;
-                    if (ok) {
-                        const float v = exact_metric_f32<F4>(M, a[qq], row);
-                        if (v < tau[qq]) {
-                            const size_t col = (size_t)qq * KNN_THREADS + tid;
-                            int p = kc - 1;
-                            while (p > 0 && lv[(size_t)(p - 1) * LS + col] > v) {
-                                lv[(size_t)p * LS + col] = lv[(size_t)(p - 1) * LS + col];
-                                li[(size_t)p * LS + col] = li[(size_t)(p - 1) * LS + col];
-                                --p;
-                            }
-                            lv[(size_t)p * LS + col] = v;
-                            li[(size_t)p * LS + col] = (int)id;
-                            tau[qq] = lv[(size_t)(kc - 1) * LS + col];
-                            if (tau[qq] < CUDART_INF_F) {
-                                const float tf = (M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau[qq] * tau[qq] : tau[qq];
-                                thr[qq] = tf * (1.f + KNN_SLACK) - Aq[qq];
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && t + KNN_STAGES < n_tiles) issue(t + KNN_STAGES);
-    }
-
-    // ---- write the candidate columns ----------------------------------------
-#pragma unroll
-    for (int qq = 0; qq < Q; ++qq) {
-        if (!qvalid[qq]) continue;
-        const int64_t qi = q_first + qq * KNN_THREADS + tid;
-        const size_t col = (size_t)qq * KNN_THREADS + tid;
-        const size_t o = ((size_t)qi * A.n_splits + blockIdx.y) * kc;
-        for (int c = 0; c < kc; ++c) {
-            A.out_idx[o + c] = li[(size_t)c * LS + col];
-            A.out_val[o + c] = lv[(size_t)c * LS + col];
-        }
-    }
-}
-
-// merge n_splits sorted candidate lists per query into one list of kc and convert
-// the list-domain value to a distance
-__global__ void __launch_bounds__(128)
-knn_merge_kernel(const int32_t* __restrict__ in_idx, const float* __restrict__ in_val, int64_t n_query, int n_splits,
-                 int kc, int kind, int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_query; q += (int64_t)gridDim.x * blockDim.x) {
-        int head[32];
-        for (int s = 0; s < n_splits; ++s) head[s] = 0;
-        const int32_t* bi = in_idx + (size_t)q * n_splits * kc;
-        const float* bv = in_val + (size_t)q * n_splits * kc;
-        for (int c = 0; c < kc; ++c) {
-            int best = -1;
-            float bvv = CUDART_INF_F;
-            int bid = -1;
-            for (int s = 0; s < n_splits; ++s) {
-                if (head[s] >= kc) continue;
-                const int id = bi[s * kc + head[s]];
-                if (id < 0) continue;
-                const float v = bv[s * kc + head[s]];
-                if (best < 0 || v < bvv || (v == bvv && id < bid)) {
-                    best = s;
-                    bvv = v;
-                    bid = id;
-                }
-            }
-            if (best >= 0) head[best]++;
-            out_idx[(size_t)q * kc + c] = bid;
-            if (out_dist) {
-                float d = bvv;
-                if (best >= 0 && kind == MMMP_METRIC_L2) d = sqrtf(bvv);
-                out_dist[(size_t)q * kc + c] = d;
-            }
-        }
-    }
-}
-
-#endif  // superseded by knn_scan.cu
 
 // ---- fp64 re-rank ------------------------------------------------------------
 // distance in the reference's arithmetic:
@@ -504,88 +234,9 @@ int fill_metric(const mmmp_metric* m, int ldf, MetricDev& M) {
     return MMMP_OK;
 }
 
-#if 0  // superseded by knn_scan.cu
-template <int F4, int Q>
-int launch_scan(KnnArgs& A, int n_qblocks, size_t smem, void* stream) {
-    MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(n_qblocks, A.n_splits, 1);
-    MMMP_LAUNCH((knn_scan_kernel<F4, Q>), grid, KNN_THREADS, smem, stream, A);
-    MMMP_LAUNCH_CHECK();
-    return MMMP_OK;
-}
-#endif
 
 }  // namespace
 
-#if 0  // superseded by knn_scan.cu
-extern "C" int mmmp_knn(const float* ref, int64_t n_ref, const float* query, int64_t n_query, int ldf,
-                        const mmmp_metric* metric, int k, int exclude_self, int causal, int64_t query_id0,
-                        int32_t* out_idx, float* out_dist, void* stream) {
-    if (!ref || !query || !out_idx || n_ref < 0 || n_query < 0 || k < 1 || k > MMMP_MAX_K) return MMMP_ERR_ARG;
-    if (ldf < 4 || (ldf & 3) || ldf > 32) return MMMP_ERR_ARG;
-    if ((((uintptr_t)ref) & 15) || (((uintptr_t)query) & 15)) return MMMP_ERR_ARG;
-    KnnArgs A;
-    int rc = fill_metric(metric, ldf, A.M);
-    if (rc) return rc;
-    if (n_query == 0) return MMMP_OK;
-    const int F4 = f4_for(ldf);
-    if (!F4) return MMMP_ERR_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    int dev = 0, sms = 148;
-    MMMP_CUDA_TRY(cudaGetDevice(&dev));
-    MMMP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // queries per thread: 2 when there are enough queries to fill the chip twice over
-    const int Q = (n_query >= (int64_t)sms * KNN_THREADS * 2 * 2 && F4 <= 4) ? 2 : 1;
-    const int n_qblocks = mmmp_div_up(n_query, (int64_t)KNN_THREADS * Q);
-    const int64_t total_tiles = (n_ref + KNN_TILE - 1) / KNN_TILE;
-    int n_splits = 1;
-    if (n_qblocks < 2 * sms) {
-        n_splits = (2 * sms + n_qblocks - 1) / n_qblocks;
-        if (n_splits > 32) n_splits = 32;
-        if (n_splits > total_tiles) n_splits = (int)(total_tiles > 0 ? total_tiles : 1);
-    }
-    A.ref = ref;
-    A.query = query;
-    A.n_ref = n_ref;
-    A.n_query = n_query;
-    A.query_id0 = query_id0;
-    A.ldf = ldf;
-    A.kc = k;
-    A.exclude_self = exclude_self;
-    A.causal = causal;
-    A.n_splits = n_splits;
-    A.tiles_per_split = (int)((total_tiles + n_splits - 1) / n_splits);
-    if (A.tiles_per_split < 1) A.tiles_per_split = 1;
-    int32_t* tmp_idx = nullptr;
-    float* tmp_val = nullptr;
-    const size_t n_out = (size_t)n_query * n_splits * k;
-    MMMP_CUDA_TRY(cudaMallocAsync(&tmp_idx, n_out * sizeof(int32_t), s));
-    MMMP_CUDA_TRY(cudaMallocAsync(&tmp_val, n_out * sizeof(float), s));
-    A.out_idx = tmp_idx;
-    A.out_val = tmp_val;
-    const size_t smem = (size_t)KNN_STAGES * KNN_TILE * ldf * 4 + (size_t)KNN_STAGES * KNN_TILE * 4 +
-                        (size_t)k * KNN_THREADS * Q * 8 + KNN_STAGES * 8 + 16;
-    if (F4 == 1 && Q == 2) rc = launch_scan<1, 2>(A, n_qblocks, smem, stream);
-    else if (F4 == 1) rc = launch_scan<1, 1>(A, n_qblocks, smem, stream);
-    else if (F4 == 2 && Q == 2) rc = launch_scan<2, 2>(A, n_qblocks, smem, stream);
-    else if (F4 == 2) rc = launch_scan<2, 1>(A, n_qblocks, smem, stream);
-    else if (F4 == 4 && Q == 2) rc = launch_scan<4, 2>(A, n_qblocks, smem, stream);
-    else if (F4 == 4) rc = launch_scan<4, 1>(A, n_qblocks, smem, stream);
-    else rc = launch_scan<8, 1>(A, n_qblocks, smem, stream);
-    if (rc == MMMP_OK) {
-        int g = mmmp_div_up(n_query, 128);
-        if (g > sms * 8) g = sms * 8;
-        MMMP_LAUNCH(knn_merge_kernel, g, 128, 0, stream, tmp_idx, tmp_val, n_query, n_splits, k, A.M.kind, out_idx,
-                    out_dist);
-        cudaError_t e = cudaPeekAtLastError();
-        if (e != cudaSuccess) rc = MMMP_ERR_CUDA_BASE + (int)e;
-    }
-    cudaFreeAsync(tmp_idx, s);
-    cudaFreeAsync(tmp_val, s);
-    return rc;
-}
-
-#endif
 
 extern "C" int mmmp_knn_refine(const double* ref64, const double* query64, int ld64, const mmmp_metric* metric,
                                const int32_t* cand_idx, const float* cand_dist, int64_t n_query, int kc, int k,

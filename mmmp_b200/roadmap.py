@@ -101,7 +101,12 @@ class RoadmapBuilder:
         else:
             self.rank, self.size = 0, 1
         self.timer = timer
-        lim = np.array(world.robots[robot].model["joint_limits"], dtype=np.float64)
+        if robot < 0:   # composite rows of all robots (coupled planners, coupled_prm.py:88-109): L2 metric
+            if metric != "l2":
+                raise ValueError("composite roadmaps use the joint-space L2 metric (general_distance)")
+            lim = np.concatenate([np.array(r.model["joint_limits"], dtype=np.float64) for r in world.robots])
+        else:
+            lim = np.array(world.robots[robot].model["joint_limits"], dtype=np.float64)
         self.lo, self.hi = lim[:, 0].copy(), lim[:, 1].copy()
         self.D = lim.shape[0]
         self.accept_rate = None

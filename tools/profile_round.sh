@@ -22,5 +22,6 @@ python tools/edge_probe.py 1000000 > $O/plain_edge.log 2>&1 &&
       python tools/edge_probe.py 1000000 > $O/ncu_edge.log 2>&1
 python tools/disagreement.py 20000 > $O/${R}_disagreement.txt 2> $O/disagreement.err
 python tools/phase_probe.py 1000000 > $O/${R}_phase_probe.txt 2>&1
+python tools/configs_probe.py > $O/${R}_configs_probe.txt 2>&1
 tail -2 $O/${R}_bench_1gpu.err
 head -c 600 $O/${R}_bench_1gpu.json

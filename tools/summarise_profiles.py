@@ -100,7 +100,7 @@ launch_list()
 full(f"{R}_knn_scan.ncu-rep", f"{R}_knn_scan_full.csv")
 full(f"{R}_edge.ncu-rep", f"{R}_edge_full.csv")
 for name in (f"{R}_bench_1gpu.json", f"{R}_bench_reference.json", f"{R}_bench_2gpu.json", f"{R}_disagreement.txt",
-             f"{R}_phase_probe.txt"):
+             f"{R}_phase_probe.txt", f"{R}_configs_probe.txt", f"{R}_bench_4gpu.json", f"{R}_bench_8gpu.json"):
     p = os.path.join(SRC, name)
     if os.path.exists(p) and os.path.getsize(p) > 0:
         shutil.copy(p, os.path.join(DST, name))
