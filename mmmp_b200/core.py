@@ -299,6 +299,14 @@ class Features:
     def rows(self, lo: int, hi: int) -> "Features":
         return Features(self.filt[lo:hi], self.x32[lo:hi], self.x64[lo:hi], self.m32, self.m64, self.fdim)
 
+    def take(self, index: torch.Tensor) -> "Features":
+        """The rows `index` (int tensor), gathered into contiguous row sets."""
+        i = index.long()
+        same = self.filt.data_ptr() == self.x32.data_ptr()
+        x32 = self.x32[i].contiguous()
+        return Features(x32 if same else self.filt[i].contiguous(), x32, self.x64[i].contiguous(), self.m32, self.m64,
+                        self.fdim)
+
     def __len__(self):
         return self.x32.shape[0]
 

@@ -169,24 +169,28 @@ class RoadmapBuilder:
         lo, hi = shard_rows(n, self.rank, self.size)
         feats = self.features(q64, q32)
         self._mark("features")
-        # the fp32 scan keeps k + knn_pad candidates for the fp64 re-rank; rows the re-rank cannot
-        # separate from the last candidate (`ambiguous`, ~1e-8 per query at pad 2) trigger one
-        # repeat of the scan with k + 16 candidates
-        kc, kc_wide = min(self.k + self.knn_pad, 64), min(self.k + 16, 64)
-
-        def scan(kc_):
-            if self.size == 1:
-                ci, cd = core.knn(feats, feats, kc_, exclude_self=True, causal=False)
-                return None, ci, cd, feats.x64
-            r, ci, cd = core.knn_shard(feats, kc_, self.rank, self.size, exclude_self=True)
-            return r, ci, cd, core.gather_rows(feats.x64, r)
-
-        rows, ci, cd, mine64 = scan(kc)
+        # the fp32 scan keeps k + knn_pad candidates for the fp64 re-rank; the few rows the re-rank
+        # cannot separate from the last candidate (`ambiguous`, ~1e-8 per query at pad 2) are
+        # searched again, alone, with k + 16 candidates
+        kc, kc_wide = min(self.k + self.knn_pad, 64), min(self.k + 16, 63)
+        if self.size == 1:
+            rows, mine64 = None, feats.x64
+            ci, cd = core.knn(feats, feats, kc, exclude_self=True, causal=False)
+        else:
+            rows, ci, cd = core.knn_shard(feats, kc, self.rank, self.size, exclude_self=True)
+            mine64 = core.gather_rows(feats.x64, rows)
         self._mark("knn_scan")
         idx, dist, amb = core.knn_refine(feats.x64, mine64, feats.m64, ci, cd, self.k)
         if kc < kc_wide and bool(amb.any()):
-            rows, ci, cd, mine64 = scan(kc_wide)
-            idx, dist, amb = core.knn_refine(feats.x64, mine64, feats.m64, ci, cd, self.k)
+            bad = amb.nonzero().flatten()                       # positions in this rank's tables
+            ids = bad if rows is None else rows.long()[bad]     # their row ids
+            sub = feats.take(ids)
+            ci2, cd2 = core.knn(feats, sub, kc_wide + 1, exclude_self=False)   # self comes back at distance 0 ...
+            keep = ci2 != ids.to(torch.int32)[:, None]                          # ... and is dropped here
+            order = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)[:, :kc_wide]
+            ci2, cd2 = torch.gather(ci2, 1, order).contiguous(), torch.gather(cd2, 1, order).contiguous()
+            idx2, dist2, amb2 = core.knn_refine(feats.x64, sub.x64, feats.m64, ci2, cd2, self.k)
+            idx[bad], dist[bad], amb[bad] = idx2, dist2, amb2
         self._mark("knn_rerank")
         if rows is not None:   # spatial slices -> the caller's row order, on every rank
             cap = (-(-(-(-n // 128)) // self.size) + 1) * 128          # rows a shard can hold (core.knn_shard)

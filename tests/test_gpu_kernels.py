@@ -413,6 +413,34 @@ def test_empty_and_tiny_inputs(core, panda_model, cuda):
     assert (seen == 1).all()
 
 
+def test_ambiguous_rows_are_searched_again(core, panda_model, cuda):
+    """RoadmapBuilder keeps k + 2 fp32 candidates; rows whose rank k cannot be told from the last
+    candidate (exact ties here: 3000 rows on a 21 x 21 lattice, hundreds of duplicates) are
+    searched again alone with k + 16.  The distances must be the k smallest float64 ones."""
+    from mmmp_b200.roadmap import RoadmapBuilder
+    rng = np.random.default_rng(17)
+    q = np.tile(np.array([[0.0, -0.5, 0.0, -2.0, 0.0, 1.6, 0.8]]), (3000, 1))
+    q[:, [1, 3]] += np.round(rng.uniform(-0.1, 0.1, (3000, 2)), 2)
+    q64 = core.to_device_f64(q)
+    q32 = core.pack_f32(q64)
+    w = core.SpatialWorld([core.RobotSpec(panda_model, core.base_matrix((0, 0, 0.01)))], [])
+    for metric in ("l2", "fk"):
+        out = RoadmapBuilder(w, 0, metric, 10, 20, 0.05, knn_pad=2, single_rank=True).candidates(q64, q32)
+        dist = _np(out["dist"])
+        if metric == "l2":
+            D = np.sqrt(((q[:, None, :] - q[None, :, :]) ** 2).sum(-1))
+        else:
+            from oracle import chain
+            P = chain.panda_positions(q, core.base_matrix((0, 0, 0.01)))
+            D = np.stack([np.sqrt(((P[i:i + 1] - P) ** 2).sum(-1)).sum(-1) for i in range(len(q))])
+        np.fill_diagonal(D, np.inf)
+        ref = np.sort(D, 1)[:, :10]
+        assert np.abs(dist - ref).max() < 1e-9
+        idx = _np(out["idx"])
+        assert (idx != np.arange(len(q))[:, None]).all()            # self never comes back as a neighbour
+        assert np.abs(np.take_along_axis(D, idx, 1) - ref).max() < 1e-9   # the ids carry those distances
+
+
 def test_knn_causal_and_queries_subset(core, cuda):
     rng = np.random.default_rng(5)
     q = np.round(rng.uniform(-3, 3, (4000, 4)), 2)

@@ -14,9 +14,9 @@ python bench.py --steps 1 --warmup 1 --nodes 250000 --no-cpu > $O/plain_launches
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${R}_launches_raw.csv \
       python bench.py --steps 1 --warmup 1 --nodes 250000 --no-cpu > $O/ncu_launches.log 2>&1
 # full captures of the two dominant kernels at the bench size
-python tools/knn_one.py 1000000 fk 1 > $O/plain_knn.log 2>&1 &&
+python tools/knn_one.py 1000000 fk 1 12 > $O/plain_knn.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:knn_scan_kernel -c 1 -f -o $O/${R}_knn_scan \
-      python tools/knn_one.py 1000000 fk 1 > $O/ncu_knn.log 2>&1
+      python tools/knn_one.py 1000000 fk 1 12 > $O/ncu_knn.log 2>&1
 python tools/edge_probe.py 1000000 > $O/plain_edge.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k "regex:collide_edges_(adaptive|hard)" -c 2 -f -o $O/${R}_edge \
       python tools/edge_probe.py 1000000 > $O/ncu_edge.log 2>&1
