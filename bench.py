@@ -366,7 +366,7 @@ def run_ours(args):
         s_eff = counters["evals_per_edge"] if counters else None
         roof = {"bound": "hbm", "kernel": "knn_scan_kernel<1,1>", "achieved": alg_bytes / (scan_ms * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (scan_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": 347366400, "traffic_source": "ncu --set full, profiles/r01_knn_scan_full.csv "
+                "traffic": 408216320, "traffic_source": "ncu --set full, profiles/r01_knn_scan_full.csv "
                                                         "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                 "peak_source": peak_src, "ms_per_launch": scan_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "executed": executed,
