@@ -9,8 +9,9 @@ per arm, k = 10 nearest candidates under the reference's FK metric
 (local_step 0.02).  One step = the whole learning phase for all arms:
 sample -> config collision -> compaction -> FK features -> k-NN scan + fp64 re-rank
 -> edge collision, all device resident.  With N GPUs the total work is fixed (strong
-scaling): every rank owns a contiguous block of candidate samples / query rows and the
-blocks are exchanged with NCCL all-gather.
+scaling): every rank draws a block of the candidate stream, answers one spatial slice of the
+neighbour search and checks one row block of the candidate edges; the pieces are exchanged
+with NCCL all-gather.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
