@@ -56,7 +56,10 @@ constexpr int KNN_THREADS = KNN_CTHREADS + 32; // + producer warp
 #endif
 constexpr int KNN_STAGES = MMMP_KNN_STAGES;
 constexpr int KNN_DU = MMMP_KNN_DU;            // drain: exact evaluations in flight per lane
-constexpr int KNN_TILE = 128;                  // reference rows per shared-memory tile
+#ifndef MMMP_KNN_TILE
+#define MMMP_KNN_TILE 128
+#endif
+constexpr int KNN_TILE = MMMP_KNN_TILE;        // reference rows per shared-memory tile
 #ifndef MMMP_KNN_RU
 #define MMMP_KNN_RU 8
 #endif
