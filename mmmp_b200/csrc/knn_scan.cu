@@ -45,7 +45,10 @@
 
 namespace {
 
-constexpr int KNN_CWARPS = 4;                  // consumer warps per CTA
+#ifndef MMMP_KNN_CWARPS
+#define MMMP_KNN_CWARPS 4
+#endif
+constexpr int KNN_CWARPS = MMMP_KNN_CWARPS;    // consumer warps per CTA
 constexpr int KNN_CTHREADS = KNN_CWARPS * 32;  // consumer threads
 constexpr int KNN_THREADS = KNN_CTHREADS + 32; // + producer warp
 #ifndef MMMP_KNN_STAGES
