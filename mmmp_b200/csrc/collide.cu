@@ -29,6 +29,12 @@
 namespace {
 
 #define MMMP_GAP_SLACK 1.0e-4f   // metres: clearance kept in hand when a step is skipped
+#ifndef MMMP_EDGE_LANES
+#define MMMP_EDGE_LANES 4          // lanes per edge in the step-skipping pass (4: 8 edges per warp)
+#endif
+#ifndef MMMP_EDGE_DEFER_ROUNDS
+#define MMMP_EDGE_DEFER_ROUNDS 2    // rounds after which an edge may still be handed to the second pass
+#endif
 
 struct SpatialSmem {
     int n_r;
@@ -631,7 +637,7 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
         // An edge on which the first rounds prove little (clearance below the travel per step) will
         // have nearly every step evaluated: hand it, with its undecided steps, to the warp-per-edge
         // pass that follows (coherent lanes, verdict-only evaluation).
-        const bool defer = hard_edge && mask != 0 && rounds <= 2 && __popcll(mask) > hard_after;
+        const bool defer = hard_edge && mask != 0 && rounds <= MMMP_EDGE_DEFER_ROUNDS && __popcll(mask) > hard_after;
         const unsigned db = __ballot_sync(FULL, defer && gl == 0);
         if (db) {
             unsigned long long base = 0;
@@ -890,7 +896,7 @@ static int launch_edges(const mmmp_world* w, int robot, const float* qa, const f
         grid = mmmp_div_up(E, wpc) < grid ? mmmp_div_up(E, wpc) : grid;
         MMMP_LAUNCH(collide_edges_kernel, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps, step, out);
     } else {
-        constexpr int L = 4;
+        constexpr int L = MMMP_EDGE_LANES;
         rc = pick_launch(collide_edges_adaptive_kernel<L>, w, A, 4 * (32 / L) * 8, E, block, smem, grid);
         if (rc) return rc;
         // clearance a lane asks for = (its share of the undecided steps) * step * refine.  Measured on
