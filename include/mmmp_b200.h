@@ -284,6 +284,16 @@ int mmmp_knn_shard(const float* fref_d, const float* xref_d, int64_t n_ref, int 
                    int n_shards, int32_t* out_rows_d, int64_t* n_rows_h, int32_t* out_idx_d,
                    float* out_dist_d, void* stream);
 
+/* The same with explicit cuts: the query blocks [floor(B * frac_lo), floor(B * frac_hi))
+ * of the B = ceil(n / 128) blocks of the scan order (0 <= frac_lo <= frac_hi <= 1).  Ranks
+ * that use the cuts c_0 = 0 < c_1 < ... < c_G = 1 answer every row exactly once; moving the
+ * cuts balances ranks whose slices cost differently (RoadmapBuilder adapts them from the
+ * measured scan times).  cap >= (ceil(B * (frac_hi - frac_lo)) + 1) * 128.                 */
+int mmmp_knn_range(const float* fref_d, const float* xref_d, int64_t n_ref, int ldf, int fdim,
+                   int ldx, const mmmp_metric* metric, int k, int exclude_self, double frac_lo,
+                   double frac_hi, int32_t* out_rows_d, int64_t* n_rows_h, int32_t* out_idx_d,
+                   float* out_dist_d, void* stream);
+
 /* profiling aid: enable != 0 turns on five device counters of the scan kernel
  * (exact evaluations, list insertions, warp drains, tiles loaded, most tiles
  * loaded by one CTA); out5_h (may be NULL) receives and resets them;

@@ -113,6 +113,7 @@ SIGNATURES = {
     "mmmp_gather_rows": [_P, _I, _P, _I64, _P, _P],
     "mmmp_knn": [_P, _P, _I64, _P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _I, _I64, _P, _P, _P],
     "mmmp_knn_shard": [_P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "mmmp_knn_range": [_P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _D, _D, _P, _P, _P, _P, _P],
     "mmmp_knn_stats": [_I, _P],
     "mmmp_edge_stats": [_I, _P],
     "mmmp_knn_refine": [_P, _P, _I, C.POINTER(Metric), _P, _P, _I64, _I, _I, _D, _P, _P, _P, _P],

@@ -357,6 +357,24 @@ def knn_shard(ref: Features, k: int, shard: int, n_shards: int, exclude_self: bo
     return rows[:m.value], idx[:m.value], dist[:m.value]
 
 
+def knn_range(ref: Features, k: int, frac_lo: float, frac_hi: float, exclude_self: bool = True):
+    """knn_shard with explicit cuts: the query blocks [floor(B frac_lo), floor(B frac_hi)) of the
+    B = ceil(n / 128) blocks of the scan order (mmmp_knn_range) -> (rows, idx, dist)."""
+    fr, xr = _dev(ref.filt, torch.float32), _dev(ref.x32, torch.float32)
+    n = fr.shape[0]
+    blocks = -(-n // 128)
+    cap = (int(np.ceil(blocks * max(frac_hi - frac_lo, 0.0))) + 2) * 128
+    rows = torch.empty((cap,), dtype=torch.int32, device=fr.device)
+    idx = torch.empty((cap, k), dtype=torch.int32, device=fr.device)
+    dist = torch.empty((cap, k), dtype=torch.float32, device=fr.device)
+    m = C.c_int64(0)
+    fdim = ref.fdim or ref.m32.dim
+    _lib.call("mmmp_knn_range", _ptr(fr), _ptr(xr), n, fr.shape[1], fdim, xr.shape[1], C.byref(ref.m32), k,
+              int(exclude_self), float(frac_lo), float(frac_hi), _ptr(rows), C.byref(m), _ptr(idx), _ptr(dist),
+              _stream())
+    return rows[:m.value], idx[:m.value], dist[:m.value]
+
+
 def knn_refine(ref64: torch.Tensor, query64: torch.Tensor, metric64: Metric, cand_idx: torch.Tensor,
                cand_dist: torch.Tensor, k: int, tie_eps: float = 1e-6):
     """fp64 re-rank -> (idx [nq, k], dist64 [nq, k], ambiguous [nq] u8)."""

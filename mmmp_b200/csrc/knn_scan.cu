@@ -855,12 +855,13 @@ extern "C" int mmmp_knn_stats(int enable, unsigned long long* out5_h) {
     return MMMP_OK;
 }
 
-// shard >= 0: the queries are the references and only the query blocks of shard `shard` of
-// `n_shards` (contiguous in scan order) are searched; output rows are compact (out_rows names
+// frac_lo >= 0: the queries are the references and only the query blocks
+// [floor(B * frac_lo), floor(B * frac_hi)) of the B blocks of the scan order are searched;
+// output rows are compact (out_rows names
 // the original row of each) and *n_rows_h receives their number
 static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const float* fquery, const float* xquery,
                     int64_t n_query, int ldf, int fdim, int ldx, const mmmp_metric* metric, int k, int exclude_self,
-                    int causal, int64_t query_id0, int shard, int n_shards, int32_t* out_rows, int64_t* n_rows_h,
+                    int causal, int64_t query_id0, double frac_lo, double frac_hi, int32_t* out_rows, int64_t* n_rows_h,
                     int32_t* out_idx, float* out_dist, void* stream) {
     if (!fref || !xref || !fquery || !xquery || !out_idx || n_ref < 0 || n_query < 0 || k < 1 || k > MMMP_MAX_K)
         return MMMP_ERR_ARG;
@@ -882,7 +883,8 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     // queries per thread: measured on B200 (1M x 1M, FK and joint-space metrics), one query per
     // thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM
-    const int qmax = (F4 <= 2 && shard < 0) ? 2 : 1;
+    const bool ranged = frac_lo >= 0.0;
+    const int qmax = (F4 <= 2 && !ranged) ? 2 : 1;
     int Q = 1;
     if (const char* e = getenv("MMMP_KNN_Q")) {
         const int q = atoi(e);
@@ -895,9 +897,13 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     const int all_qblocks = mmmp_div_up(n_query, (int64_t)KNN_CTHREADS * Q);
     int qblock0 = 0, n_qblocks = all_qblocks;
     int64_t n_rows = n_query;  // rows this launch answers
-    if (shard >= 0) {
-        qblock0 = (int)((int64_t)all_qblocks * shard / n_shards);
-        n_qblocks = (int)((int64_t)all_qblocks * (shard + 1) / n_shards) - qblock0;
+    if (ranged) {
+        qblock0 = (int)((double)all_qblocks * frac_lo);
+        int qblock1 = frac_hi >= 1.0 ? all_qblocks : (int)((double)all_qblocks * frac_hi);
+        if (qblock0 > all_qblocks) qblock0 = all_qblocks;
+        if (qblock1 > all_qblocks) qblock1 = all_qblocks;
+        if (qblock1 < qblock0) qblock1 = qblock0;
+        n_qblocks = qblock1 - qblock0;
         const int64_t first = (int64_t)qblock0 * KNN_CTHREADS * Q, end = ((int64_t)qblock0 + n_qblocks) * KNN_CTHREADS * Q;
         n_rows = (end < n_query ? end : n_query) - first;
         if (n_rows < 0) n_rows = 0;
@@ -988,7 +994,7 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     A.flags = (exclude_self ? 1 : 0) | (causal ? 2 : 0) | ((same && query_id0 == 0) ? 4 : 0);
     A.n_splits = n_splits;
     A.qblock0 = qblock0;
-    A.out_rows = shard >= 0 ? out_rows : nullptr;
+    A.out_rows = ranged ? out_rows : nullptr;
     A.tiles_per_split = (int)((total_tiles + n_splits - 1) / n_splits);
     if (A.tiles_per_split < 1) A.tiles_per_split = 1;
     A.stats = g_knn_stats;
@@ -1021,13 +1027,22 @@ extern "C" int mmmp_knn(const float* fref, const float* xref, int64_t n_ref, con
                         int k, int exclude_self, int causal, int64_t query_id0, int32_t* out_idx, float* out_dist,
                         void* stream) {
     return knn_impl(fref, xref, n_ref, fquery, xquery, n_query, ldf, fdim, ldx, metric, k, exclude_self, causal,
-                    query_id0, -1, 1, nullptr, nullptr, out_idx, out_dist, stream);
+                    query_id0, -1.0, -1.0, nullptr, nullptr, out_idx, out_dist, stream);
+}
+
+extern "C" int mmmp_knn_range(const float* fref, const float* xref, int64_t n_ref, int ldf, int fdim, int ldx,
+                              const mmmp_metric* metric, int k, int exclude_self, double frac_lo, double frac_hi,
+                              int32_t* out_rows, int64_t* n_rows_h, int32_t* out_idx, float* out_dist, void* stream) {
+    if (!(frac_lo >= 0.0) || !(frac_hi >= frac_lo) || frac_hi > 1.0 || !out_rows || !n_rows_h) return MMMP_ERR_ARG;
+    return knn_impl(fref, xref, n_ref, fref, xref, n_ref, ldf, fdim, ldx, metric, k, exclude_self, 0, 0, frac_lo, frac_hi,
+                    out_rows, n_rows_h, out_idx, out_dist, stream);
 }
 
 extern "C" int mmmp_knn_shard(const float* fref, const float* xref, int64_t n_ref, int ldf, int fdim, int ldx,
                               const mmmp_metric* metric, int k, int exclude_self, int shard, int n_shards,
                               int32_t* out_rows, int64_t* n_rows_h, int32_t* out_idx, float* out_dist, void* stream) {
-    if (shard < 0 || n_shards < 1 || shard >= n_shards || !out_rows || !n_rows_h) return MMMP_ERR_ARG;
-    return knn_impl(fref, xref, n_ref, fref, xref, n_ref, ldf, fdim, ldx, metric, k, exclude_self, 0, 0, shard,
-                    n_shards, out_rows, n_rows_h, out_idx, out_dist, stream);
+    if (shard < 0 || n_shards < 1 || shard >= n_shards) return MMMP_ERR_ARG;
+    return mmmp_knn_range(fref, xref, n_ref, ldf, fdim, ldx, metric, k, exclude_self, (double)shard / n_shards,
+                          shard + 1 == n_shards ? 1.0 : (double)(shard + 1) / n_shards, out_rows, n_rows_h, out_idx,
+                          out_dist, stream);
 }

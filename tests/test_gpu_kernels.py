@@ -373,6 +373,17 @@ def test_knn_shards_tile_the_unsharded_search(core, panda_model, cuda):
                     seen[rows.long()] += 1
                     assert (idx == ref_i[rows.long()]).all() and (dist == ref_d[rows.long()]).all()
                 assert (seen == 1).all()
+            # mmmp_knn_range: uneven cuts (the ones RoadmapBuilder adapts to measured scan times),
+            # including an empty slice, tile the search the same way
+            cuts = [0.0, 0.07, 0.07, 0.41, 0.93, 1.0]
+            seen = torch.zeros(n, dtype=torch.int32, device=cuda)
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                rows, idx, dist = core.knn_range(F, 12, lo, hi)
+                if lo == hi:
+                    assert rows.numel() == 0
+                seen[rows.long()] += 1
+                assert (idx == ref_i[rows.long()]).all() and (dist == ref_d[rows.long()]).all()
+            assert (seen == 1).all()
 
 
 def test_empty_and_tiny_inputs(core, panda_model, cuda):
