@@ -147,7 +147,6 @@ __device__ __forceinline__ void load_frame(Affine& T, const float* fr, int strid
     for (int i = 0; i < 12; ++i) T.m[i] = p[i * stride];
 }
 
-__device__ __forceinline__ float fast_sqrt(float x) { return x * rsqrtf(fmaxf(x, 1e-30f)); }
 
 // spheres of link lb (robot RB, pose TB) against spheres of link la (robot RA, pose TA); the
 // caller has already found the two bounding spheres overlapping (GAP: closer than `want`).

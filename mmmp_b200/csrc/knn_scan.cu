@@ -101,6 +101,38 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+#ifndef MMMP_KNN_SPIN_NS
+#define MMMP_KNN_SPIN_NS 0   // measured: 256 ns of sleep per poll costs 4 % (late pushes), the plain loop stays
+#endif
+// the producer's wait for a free ring slot.  The try_wait loop above re-issues every ~26 cycles
+// and accounts for 38 % of the kernel's executed instructions (profiles/r01_knn_scan_full.csv),
+// but the issue slots it takes are idle ones: polling with a sleep (MMMP_KNN_SPIN_NS > 0) frees
+// them and still loses, because every push then starts late.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+#if MMMP_KNN_SPIN_NS > 0
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(MMMP_KNN_SPIN_NS);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {  // MUFU.RSQ without the denormal fix-up
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -299,7 +331,7 @@ __device__ __forceinline__ float exact_metric(const MetricDev& M, const float* a
                 const float dx = a[(3 * g) * as] - b[3 * g], dy = a[(3 * g + 1) * as] - b[3 * g + 1],
                             dz = a[(3 * g + 2) * as] - b[3 * g + 2];
                 const float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                v = fmaf(M.w[g], s2 * rsqrtf(fmaxf(s2, 1e-30f)), v);  // candidates are re-ranked in fp64
+                v = fmaf(M.w[g], s2 * rsqrt_ftz(fmaxf(s2, 1e-30f)), v);  // candidates are re-ranked in fp64
             }
         }
     } else {
@@ -326,6 +358,7 @@ struct ScanCtl {                  // per-CTA control block in shared memory
     float wbox[KNN_CWARPS][6];    // query box of every consumer warp
     volatile float wtau[KNN_CWARPS];  // worst (largest) filter-domain bound of every consumer warp
     volatile int tile_id[KNN_STAGES];
+    float tbox[KNN_STAGES][6];    // box of the tile in every stage (written by the producer with tile_id)
     int pre[KNN_CWARPS][33];      // drain: exclusive prefix of the lanes' queue lengths
 };
 
@@ -436,11 +469,14 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
         const int lane = tid & 31;
         int slot = 0;
         unsigned long long loaded = 0;
-        auto push = [&](int64_t t) {  // t < 0: end marker
+        auto push = [&](int64_t t, const float* tb) {  // t < 0: end marker; tb: the tile's box (lane 0) or NULL
             if (lane == 0) {
                 const int s = slot % KNN_STAGES;
-                mbar_wait(empty_s + 8 * s, ((slot / KNN_STAGES) & 1) ^ 1);
+                mbar_wait_relaxed(empty_s + 8 * s, ((slot / KNN_STAGES) & 1) ^ 1);
                 ctl->tile_id[s] = (int)t;
+                if (tb)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) ctl->tbox[s][c] = tb[c];
                 if (t < 0) {
                     mbar_arrive(full_s + 8 * s);
                 } else {
@@ -460,7 +496,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             __syncwarp();
         };
         if (!cull) {
-            for (int64_t t = tile_lo; t < tile_hi; ++t) push(t);
+            for (int64_t t = tile_lo; t < tile_hi; ++t) push(t, nullptr);
         } else {
             // outward walk from the tile that holds this CTA's own rows (queries and references
             // share the spatial order), 16 boxes per side and step; a tile is loaded only if it
@@ -482,7 +518,13 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             while (up < tile_hi || down >= tile_lo) {
                 const int64_t t = lane < 16 ? up + lane : down - (lane - 16);
                 const bool in = lane < 16 ? t < tile_hi : t >= tile_lo;
-                const float d2 = in ? box_dist2(cbox, A.boxes + t * 6) : CUDART_INF_F;
+                float tb[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) tb[c] = in ? __ldg(A.boxes + t * 6 + c) : 0.f;
+                // one test per tile against the CTA's box and its loosest bound; testing every
+                // consumer warp's own box here loads fewer tiles but was measured 6 % slower (the
+                // producer's push latency is on the consumers' critical path)
+                const float d2 = in ? box_dist2(cbox, tb) : CUDART_INF_F;
                 up += 16;
                 down -= 16;
                 float worst = 0.f;
@@ -493,18 +535,21 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     if (!((cand >> l) & 1u)) continue;
                     const int tt = __shfl_sync(0xffffffffu, (int)t, l);
                     const float dd = __shfl_sync(0xffffffffu, d2, l);
+                    float sb[6];  // the consumers' own cull test reads the box from shared memory
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) sb[c] = __shfl_sync(0xffffffffu, tb[c], l);
                     int go = 0;
-                    if (lane == 0) {
+                    if (lane == 0) {  // the bounds have tightened while earlier tiles were scanned: test again
                         float now = 0.f;
                         for (int w = 0; w < KNN_CWARPS; ++w) now = fmaxf(now, ctl->wtau[w]);
                         go = !(dd > now * (1.f + 1e-4f) + 1e-12f);
                     }
                     go = __shfl_sync(0xffffffffu, go, 0);
-                    if (go) push(tt);
+                    if (go) push(tt, sb);
                 }
             }
         }
-        push(-1);
+        push(-1, nullptr);
         if (A.stats && lane == 0) {
             atomicAdd(A.stats + 3, loaded);
             atomicMax(A.stats + 4, loaded);
@@ -525,7 +570,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     // the 32 lanes, whichever lane queued them -- exact fp32 metric of the owner's query row
     // (shared-memory column) against the tile's exact row (shared memory), value parked next
     // to the queue entry; (2) every lane walks its own values and inserts the few that beat
-    // its k-th best.  Candidate order is (value, original id): the result does not depend on
+    // its k-th best.  Candidate order is (value, scan position): the result does not depend on
     // visit order.
     auto drain = [&]() {
         const int lane = tid & 31;
@@ -577,14 +622,18 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             const int col = qq * KNN_CTHREADS + tid;
             float* lvc = lv + col;
             int* lic = li + col;
+            float tv = lvc[(kc - 1) * LS];
             for (int e = 0; e < cnt; ++e) {
                 const int at = (qq * KNN_QC + e) * KNN_CTHREADS + tid;
                 const float v = qval[at];
-                const float tv = lvc[(kc - 1) * LS];
                 if (!(v <= tv) || !(v < CUDART_INF_F)) continue;
-                const int64_t pos = tile_r0 + queue[at];
-                const int64_t id = A.perm ? (int64_t)__ldg(A.perm + pos) : pos;
-                if ((A.flags & 5) == 1 && id == A.query_id0 + qrow[qq]) continue;  // self, found by id
+                // the list holds scan POSITIONS (ties broken by position; the scan order is
+                // deterministic): the original id is looked up once, when the list is written
+                const int64_t id = tile_r0 + queue[at];
+                if ((A.flags & 5) == 1) {  // self, found by original id (queries in their own order)
+                    const int64_t orig = A.perm ? (int64_t)__ldg(A.perm + id) : id;
+                    if (orig == A.query_id0 + qrow[qq]) continue;
+                }
                 if (v == tv && (int)id >= lic[(kc - 1) * LS]) continue;
                 int p = kc - 1;
                 while (p > 0) {
@@ -598,6 +647,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                 lvc[p * LS] = v;
                 lic[p * LS] = (int)id;
                 const float tau = lvc[(kc - 1) * LS];
+                tv = tau;
                 if (tau < CUDART_INF_F) {
                     const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
                     thr[qq] = tf - Aq[qq];
@@ -629,7 +679,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
         const int cnt = (int)((ref_end - r0) < KNN_TILE ? (ref_end - r0) : KNN_TILE);
         bool skip = false;
         if (cull) {  // warp-level cull: this warp's box against the tile's box
-            const float d2 = box_dist2(ctl->wbox[warp], A.boxes + (int64_t)t * 6);
+            const float d2 = box_dist2(ctl->wbox[warp], ctl->tbox[s]);
             skip = d2 > ctl->wtau[warp] * (1.f + 1e-4f) + 1e-12f;
         }
         if (!skip) {
@@ -716,7 +766,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
         }
         for (int c = 0; c < kc; ++c) {
             const int id = li[c * LS + col];
-            A.out_idx[o + c] = id == 0x7fffffff ? -1 : id;
+            A.out_idx[o + c] = id == 0x7fffffff ? -1 : (A.perm ? __ldg(A.perm + id) : id);
             A.out_val[o + c] = lv[c * LS + col];
         }
     }

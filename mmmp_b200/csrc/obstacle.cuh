@@ -4,6 +4,15 @@
 #pragma once
 #include "common.cuh"
 
+// sqrt for CLEARANCES only (never for a verdict): x * MUFU.RSQ(x), without the denormal fix-up
+// rsqrtf() carries (6 % of the edge kernel's instructions, profiles/r01_edge_full.csv).  The
+// ~2 ulp error is far inside MMMP_GAP_SLACK.
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(x, 1e-30f)));
+    return x * y;
+}
+
 // Returns the overlap verdict.  With GAP the sphere's clearance from the primitive (distance
 // between the surfaces, meaningful when there is no overlap) is folded into `gap` by min; the
 // verdict is computed by the same expressions either way.
@@ -21,7 +30,7 @@ __device__ __forceinline__ bool sphere_vs_obstacle(float cx, float cy, float cz,
             const float dx = cx - p[0], dy = cy - p[1], dz = cz - p[2];
             const float rr = r + p[3];
             const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            if (GAP) gap = fminf(gap, sqrtf(d2) - rr);
+            if (GAP) gap = fminf(gap, fast_sqrt(d2) - rr);
             return d2 <= rr * rr;
         }
         case MMMP_OBS_BOX: {
@@ -34,7 +43,7 @@ __device__ __forceinline__ bool sphere_vs_obstacle(float cx, float cy, float cz,
             const float ey = fmaxf(fabsf(by) - p[4], 0.f);
             const float ez = fmaxf(fabsf(bz) - p[5], 0.f);
             const float e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-            if (GAP) gap = fminf(gap, sqrtf(e2) - r);
+            if (GAP) gap = fminf(gap, fast_sqrt(e2) - r);
             return e2 <= r * r;
         }
         case MMMP_OBS_CYLINDER: {
@@ -45,7 +54,7 @@ __device__ __forceinline__ bool sphere_vs_obstacle(float cx, float cy, float cz,
             const float eh = fmaxf(fabsf(h) - p[6], 0.f);
             const float er = fmaxf(rad - p[7], 0.f);
             const float e2 = fmaf(eh, eh, er * er);
-            if (GAP) gap = fminf(gap, sqrtf(e2) - r);
+            if (GAP) gap = fminf(gap, fast_sqrt(e2) - r);
             return e2 <= r * r;
         }
     }
