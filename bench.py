@@ -174,6 +174,23 @@ def workload_config(args):
             "l2": "per-step working set (>1 GB) exceeds the 126 MB L2 and a 256 MB buffer is rewritten between steps"}
 
 
+def ncu_traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the scan kernel, from the committed
+    summary of the round's `ncu --set full` capture (tools/summarise_profiles.py); None if it is missing."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    try:
+        with open(path) as f:
+            for row in f:
+                cells = row.strip().split(",")
+                if len(cells) >= 3 and cells[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(cells[2]) * scale[cells[1]]
+                    seen += 1
+    except (OSError, ValueError, KeyError):
+        return None
+    return int(total) if seen == 2 else None
+
+
 def kernel_counters(core, builder, args):
     """Library counters of one arm's scan + edge check (untimed diagnostic launch)."""
     import ctypes as C
@@ -367,7 +384,8 @@ def run_ours(args):
         s_eff = counters["evals_per_edge"] if counters else None
         roof = {"bound": "hbm", "kernel": "knn_scan_kernel<1,1>", "achieved": alg_bytes / (scan_ms * 1e-3) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (scan_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": 408216320, "traffic_source": "ncu --set full, profiles/r01_knn_scan_full.csv "
+                "traffic": ncu_traffic(os.path.join(ROOT, "profiles", "r01_knn_scan_full.csv")),
+                "traffic_source": "ncu --set full, profiles/r01_knn_scan_full.csv "
                                                         "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                 "peak_source": peak_src, "ms_per_launch": scan_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "executed": executed,

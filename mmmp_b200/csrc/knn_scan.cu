@@ -67,8 +67,17 @@ constexpr int KNN_TILE = MMMP_KNN_TILE;        // reference rows per shared-memo
 #define MMMP_KNN_RU 8
 #endif
 constexpr int KNN_RU = MMMP_KNN_RU;            // rows per inner-loop step
-constexpr int KNN_QSLACK = 12;                 // queue entries a thread may hold before its warp drains
+#ifndef MMMP_KNN_QSLACK
+#define MMMP_KNN_QSLACK 12
+#endif
+constexpr int KNN_QSLACK = MMMP_KNN_QSLACK;    // queue entries a thread may hold before its warp drains
 constexpr int KNN_QC = KNN_RU + KNN_QSLACK;    // queue capacity per (thread, query)
+#ifndef MMMP_KNN_MINB
+#define MMMP_KNN_MINB 5                        // resident CTAs per SM the register budget must allow (72 registers)
+#endif
+#ifndef MMMP_KNN_WARPQ
+#define MMMP_KNN_WARPQ 1                       // 1: one compacted queue per warp; 0: one queue per thread
+#endif
 constexpr float KNN_SLACK = 2.0e-5f;           // relative slack of the fp32 filter
 constexpr int KNN_CULL_MIN = 4096;             // references below which sorting does not pay
 
@@ -359,7 +368,9 @@ struct ScanCtl {                  // per-CTA control block in shared memory
     volatile float wtau[KNN_CWARPS];  // worst (largest) filter-domain bound of every consumer warp
     volatile int tile_id[KNN_STAGES];
     float tbox[KNN_STAGES][6];    // box of the tile in every stage (written by the producer with tile_id)
+#if !MMMP_KNN_WARPQ
     int pre[KNN_CWARPS][33];      // drain: exclusive prefix of the lanes' queue lengths
+#endif
 };
 
 // shared-memory layout (floats unless noted), LS = KNN_CTHREADS * Q:
@@ -369,7 +380,7 @@ __host__ __device__ constexpr size_t knn_stage_floats(int W, int S) { return (si
 __host__ __device__ constexpr size_t knn_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int F4, int Q>
-__global__ void __launch_bounds__(KNN_THREADS, F4 <= 2 ? 3 : 1)
+__global__ void __launch_bounds__(KNN_THREADS, F4 <= 2 ? MMMP_KNN_MINB : 1)
 knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int W = F4 * 4;
@@ -381,10 +392,18 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     float* lv = ring + KNN_STAGES * stage_floats;
     int* li = reinterpret_cast<int*>(lv + (size_t)kc * LS);
     float* xq = reinterpret_cast<float*>(li + (size_t)kc * LS);
+#if MMMP_KNN_WARPQ
+    // warp queues: [CWARPS][32 * Q * QC] entries of 16 bits, (query slot, owner lane) << 8 | tile row
+    unsigned short* wqueue = reinterpret_cast<unsigned short*>(xq + (size_t)S * LS);
+    unsigned char* queue = reinterpret_cast<unsigned char*>(wqueue);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + knn_align((size_t)(queue - smem_raw) +
+                                                                      (size_t)Q * KNN_QC * KNN_CTHREADS * 2, 8));
+#else
     float* qval = xq + (size_t)S * LS;
     unsigned char* queue = reinterpret_cast<unsigned char*>(qval + (size_t)Q * KNN_QC * KNN_CTHREADS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + knn_align((size_t)(queue - smem_raw) +
                                                                       (size_t)Q * KNN_QC * KNN_CTHREADS, 8));
+#endif
     ScanCtl* ctl = reinterpret_cast<ScanCtl*>(bars + 2 * KNN_STAGES);
     const uint32_t ring_s = smem_u32(ring);
     const uint32_t full_s = smem_u32(bars), empty_s = smem_u32(bars + KNN_STAGES);
@@ -559,12 +578,108 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
 
     // ================= consumer warps =================
     const int warp = tid >> 5;
+    const float* tile_x = nullptr;   // exact rows of the tile being scanned
+    int64_t tile_r0 = 0;
+#if MMMP_KNN_WARPQ
+    constexpr int WQ_CAP = 32 * Q * KNN_QC;
+    unsigned short* wq = wqueue + warp * WQ_CAP;
+    int wcnt = 0;  // entries in the warp's queue (warp uniform)
+    const int lane = tid & 31;
+    const unsigned lanes_below = (1u << lane) - 1u;
+
+    // Drain: the queue is a compact list of (owner, row) pairs, 32 per round, whichever lane
+    // queued them.  Exact fp32 metric of the owner's query row (shared-memory column) against
+    // the tile's exact row (shared memory); the few values that beat the owner's k-th best are
+    // inserted into the owner's list by the lane that evaluated them -- lanes that hold values
+    // for the same owner take turns (match_any).  Candidate order is (value, scan position): the
+    // result does not depend on visit order.
+    auto drain = [&]() {
+        const int wbase = warp * 32;
+        __syncwarp();
+        for (int g0 = 0; g0 < wcnt; g0 += 32) {
+            const int g = g0 + lane;
+            const bool valid = g < wcnt;
+            const unsigned ent = wq[valid ? g : 0];
+            const int j = ent & 0xff;
+            const int oq = ent >> 13, ol = (ent >> 8) & 31;
+            const int ocol = oq * KNN_CTHREADS + wbase + ol;
+            const int64_t pos = tile_r0 + j;
+            bool ok = valid && pos < ref_end;
+            if ((A.flags & 5) == 5) ok = ok && pos != q_first + ocol;  // same scan order: self = same position
+            if (A.flags & 2) ok = ok && pos < A.query_id0 + q_first + ocol;  // causal searches keep row order
+            if ((A.flags & 5) == 1) {  // self, found by original id (queries in their own order)
+                int64_t orow = 0;
+#pragma unroll
+                for (int qq = 0; qq < Q; ++qq) {
+                    const int64_t r = __shfl_sync(0xffffffffu, qrow[qq], ol);
+                    if (qq == oq) orow = r;
+                }
+                const int64_t orig = (A.perm && ok) ? (int64_t)__ldg(A.perm + pos) : pos;
+                ok = ok && orig != A.query_id0 + orow;
+            }
+            const float v = exact_metric(A.M, xq + ocol, LS, tile_x + (size_t)j * S);
+            float* lvc = lv + ocol;
+            int* lic = li + ocol;
+            bool pass = ok && v < CUDART_INF_F;
+            if (pass) {
+                const float tv = lvc[(kc - 1) * LS];
+                pass = v < tv || (v == tv && (int)pos < lic[(kc - 1) * LS]);
+            }
+            unsigned pm = __ballot_sync(0xffffffffu, pass);
+            while (pm) {
+                if (pass) {
+                    const unsigned peers = __match_any_sync(pm, ocol);
+                    if (__ffs(peers) - 1 == lane) {
+                        const float tv = lvc[(kc - 1) * LS];  // the list as it is now
+                        if (v < tv || (v == tv && (int)pos < lic[(kc - 1) * LS])) {
+                            int p = kc - 1;
+                            while (p > 0) {
+                                const float u = lvc[(p - 1) * LS];
+                                const int ui = lic[(p - 1) * LS];
+                                if (!(u > v || (u == v && ui > (int)pos))) break;
+                                lvc[p * LS] = u;
+                                lic[p * LS] = ui;
+                                --p;
+                            }
+                            lvc[p * LS] = v;
+                            lic[p * LS] = (int)pos;
+                            if (A.stats) atomicAdd(A.stats + 1, 1ull);
+                        }
+                        pass = false;
+                    }
+                }
+                __syncwarp();
+                pm = __ballot_sync(0xffffffffu, pass);
+            }
+        }
+        if (A.stats && lane == 0) atomicAdd(A.stats, (unsigned long long)wcnt);
+        wcnt = 0;
+        __syncwarp();
+        // every thread reads its own bounds back from its lists
+        float worst = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) {
+            const float tau = lv[(size_t)(kc - 1) * LS + qq * KNN_CTHREADS + tid];
+            if (tau < CUDART_INF_F) {
+                const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
+                thr[qq] = tf - Aq[qq];
+                tauf[qq] = tf;
+            }
+            worst = fmaxf(worst, tauf[qq]);
+        }
+        // publish the warp's worst bound for the producer's culling test
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0) {
+            ctl->wtau[warp] = worst;
+            if (A.stats) atomicAdd(A.stats + 2, 1ull);
+        }
+    };
+#else
     int qcnt[Q];
 #pragma unroll
     for (int qq = 0; qq < Q; ++qq) qcnt[qq] = 0;
     unsigned char* myq = queue + tid;
-    const float* tile_x = nullptr;   // exact rows of the tile being scanned
-    int64_t tile_r0 = 0;
 
     // Drain, per query slot: (1) the warp's queued (query, row) pairs are dealt out evenly over
     // the 32 lanes, whichever lane queued them -- exact fp32 metric of the owner's query row
@@ -669,6 +784,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             if (A.stats) atomicAdd(A.stats + 2, 1ull);
         }
     };
+#endif
 
     for (int slot = 0;; ++slot) {
         const int s = slot % KNN_STAGES;
@@ -727,6 +843,23 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     worst = fminf(worst, m - thr[qq]);
                 }
                 // one warp-uniform branch per step
+#if MMMP_KNN_WARPQ
+                if (__any_sync(0xffffffffu, worst <= 0.f)) {
+#pragma unroll
+                    for (int qq = 0; qq < Q; ++qq) {
+#pragma unroll
+                        for (int u = 0; u < KNN_RU; ++u) {
+                            const bool hit = sv[qq][u] <= thr[qq];
+                            const unsigned m = __ballot_sync(0xffffffffu, hit);
+                            if (hit)
+                                wq[wcnt + __popc(m & lanes_below)] =
+                                    (unsigned short)((((qq << 5) | lane) << 8) | (j + u));
+                            wcnt += __popc(m);
+                        }
+                    }
+                    if (wcnt > WQ_CAP - 32 * Q * KNN_RU) drain();  // room for one more step
+                }
+#else
                 if (__any_sync(0xffffffffu, worst <= 0.f)) {
                     int fill = 0;
 #pragma unroll
@@ -741,12 +874,17 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     }
                     if (__any_sync(0xffffffffu, fill > KNN_QSLACK)) drain();
                 }
+#endif
             }
             // the tile's exact rows leave with the tile: drain before releasing the slot
+#if MMMP_KNN_WARPQ
+            if (wcnt) drain();
+#else
             int pending = 0;
 #pragma unroll
             for (int qq = 0; qq < Q; ++qq) pending |= qcnt[qq];
             if (__any_sync(0xffffffffu, pending != 0)) drain();
+#endif
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty_s + 8 * s);
@@ -829,7 +967,7 @@ int fill_metric(const mmmp_metric* m, int ldx, MetricDev& M) {
 size_t scan_smem(int F4, int Q, int kc, int S) {
     const size_t w = F4 * 4, ls = (size_t)KNN_CTHREADS * Q;
     size_t b = (size_t)KNN_STAGES * knn_stage_floats((int)w, S) * 4 + (size_t)kc * ls * 8 + (size_t)S * ls * 4;
-    b = knn_align(b + (size_t)Q * KNN_QC * KNN_CTHREADS * 5, 8);
+    b = knn_align(b + (size_t)Q * KNN_QC * KNN_CTHREADS * (MMMP_KNN_WARPQ ? 2 : 5), 8);
     return b + 2 * KNN_STAGES * 8 + sizeof(ScanCtl) + 16;
 }
 
