@@ -75,6 +75,10 @@ constexpr int KNN_QC = KNN_RU + KNN_QSLACK;    // queue capacity per (thread, qu
 #ifndef MMMP_KNN_MINB
 #define MMMP_KNN_MINB 5                        // resident CTAs per SM the register budget must allow (72 registers)
 #endif
+#ifndef MMMP_KNN_WALK
+#define MMMP_KNN_WALK 2                         // producer: blocks of 16 tile boxes per side and walk step (1/2/4/8: 27.5/27.3/27.3/28.4 ms)
+#endif
+constexpr int KNN_WALK = MMMP_KNN_WALK;
 #ifndef MMMP_KNN_WARPQ
 #define MMMP_KNN_WARPQ 1                       // 1: one compacted queue per warp; 0: one queue per thread
 #endif
@@ -533,38 +537,56 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                                        (double)total_tiles);
             if (centre < tile_lo) centre = tile_lo;
             if (centre >= tile_hi) centre = tile_hi - 1;
+            // KNN_WALK blocks of 16 tiles per side and step: the boxes of a step are loaded together
+            // (one L2 latency), the blocks are then handled nearest first.  Far from the CTA's rows
+            // whole steps fail the test, and the consumers sit idle until the walk is over
             int64_t up = centre, down = centre - 1;
             while (up < tile_hi || down >= tile_lo) {
-                const int64_t t = lane < 16 ? up + lane : down - (lane - 16);
-                const bool in = lane < 16 ? t < tile_hi : t >= tile_lo;
-                float tb[6];
+                int t[KNN_WALK];
+                bool in[KNN_WALK];
+                float tb[KNN_WALK][6], d2[KNN_WALK];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) tb[c] = in ? __ldg(A.boxes + t * 6 + c) : 0.f;
+                for (int i = 0; i < KNN_WALK; ++i) {
+                    const int64_t ti = lane < 16 ? up + 16 * i + lane : down - 16 * i - (lane - 16);
+                    in[i] = lane < 16 ? ti < tile_hi : ti >= tile_lo;
+                    t[i] = (int)ti;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) tb[i][c] = in[i] ? __ldg(A.boxes + ti * 6 + c) : 0.f;
+                }
                 // one test per tile against the CTA's box and its loosest bound; testing every
                 // consumer warp's own box here loads fewer tiles but was measured 6 % slower (the
                 // producer's push latency is on the consumers' critical path)
-                const float d2 = in ? box_dist2(cbox, tb) : CUDART_INF_F;
-                up += 16;
-                down -= 16;
-                float worst = 0.f;
-                for (int w = 0; w < KNN_CWARPS; ++w) worst = fmaxf(worst, ctl->wtau[w]);
-                const unsigned cand = __ballot_sync(0xffffffffu, in && !(d2 > worst * (1.f + 1e-4f) + 1e-12f));
-                for (int r = 0; r < 32; ++r) {  // nearest first: up[0], down[0], up[1], ...
-                    const int l = (r >> 1) + ((r & 1) << 4);
-                    if (!((cand >> l) & 1u)) continue;
-                    const int tt = __shfl_sync(0xffffffffu, (int)t, l);
-                    const float dd = __shfl_sync(0xffffffffu, d2, l);
-                    float sb[6];  // the consumers' own cull test reads the box from shared memory
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) sb[c] = __shfl_sync(0xffffffffu, tb[c], l);
-                    int go = 0;
-                    if (lane == 0) {  // the bounds have tightened while earlier tiles were scanned: test again
-                        float now = 0.f;
-                        for (int w = 0; w < KNN_CWARPS; ++w) now = fmaxf(now, ctl->wtau[w]);
-                        go = !(dd > now * (1.f + 1e-4f) + 1e-12f);
+                for (int i = 0; i < KNN_WALK; ++i) d2[i] = in[i] ? box_dist2(cbox, tb[i]) : CUDART_INF_F;
+                up += 16 * KNN_WALK;
+                down -= 16 * KNN_WALK;
+#pragma unroll
+                for (int i = 0; i < KNN_WALK; ++i) {
+                    float worst = 0.f;
+                    for (int w = 0; w < KNN_CWARPS; ++w) worst = fmaxf(worst, ctl->wtau[w]);
+                    const unsigned cand =
+                        __ballot_sync(0xffffffffu, in[i] && !(d2[i] > worst * (1.f + 1e-4f) + 1e-12f));
+                    if (!cand) continue;
+                    // nearest first: up[0], down[0], up[1], ... -- bit r of `order` = lane (r >> 1) + 16 (r & 1)
+                    unsigned order = __ballot_sync(0xffffffffu, (cand >> ((lane >> 1) + ((lane & 1) << 4))) & 1u);
+                    while (order) {
+                        const int r = __ffs(order) - 1;
+                        order &= order - 1;
+                        const int l = (r >> 1) + ((r & 1) << 4);
+                        const int tt = __shfl_sync(0xffffffffu, t[i], l);
+                        const float dd = __shfl_sync(0xffffffffu, d2[i], l);
+                        float sb[6];  // the consumers' own cull test reads the box from shared memory
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) sb[c] = __shfl_sync(0xffffffffu, tb[i][c], l);
+                        int go = 0;
+                        if (lane == 0) {  // the bounds have tightened while earlier tiles were scanned: test again
+                            float now = 0.f;
+                            for (int w = 0; w < KNN_CWARPS; ++w) now = fmaxf(now, ctl->wtau[w]);
+                            go = !(dd > now * (1.f + 1e-4f) + 1e-12f);
+                        }
+                        go = __shfl_sync(0xffffffffu, go, 0);
+                        if (go) push(tt, sb);
                     }
-                    go = __shfl_sync(0xffffffffu, go, 0);
-                    if (go) push(tt, sb);
                 }
             }
         }
