@@ -28,13 +28,17 @@
 // barrier.  Every consumer thread owns Q queries (filter form in registers, exact row in a
 // shared-memory column) and reads the tile's filter rows as shared-memory broadcasts
 // (LDS.128), 8 rows per step, software pipelined.  Pairs that pass the filter are appended
-// to a small per-thread byte queue; the warp drains the queues when one is nearly full and
-// at the end of every tile: the queued pairs are dealt out evenly over the 32 lanes, exact
-// fp32 metric against the tile's exact rows -- still resident in shared memory (odd stride:
-// conflict free), so the drain never waits on a gather -- and every thread inserts the few
-// values that beat its k-th best into its sorted candidate column, which tightens its
-// threshold.  Measured on B200 (1M x 1M, FK metric): 2 stages / 8 rows / Q = 1 is the
-// fastest point of {2,3} x {4,8,16} x {1,2} (more resident CTAs beat deeper rings).
+// to one compact queue per warp (ballot + popcount; 16-bit entries: owner, tile row); the
+// warp drains it when it is nearly full and at the end of every tile, 32 pairs per round:
+// exact fp32 metric against the tile's exact rows -- still resident in shared memory (odd
+// stride: conflict free), so the drain never waits on a gather -- and the lane that
+// evaluated a value that beats the owner's k-th best inserts it into the owner's sorted
+// candidate column (shared memory); the owners read their tightened thresholds back after
+// the drain.  Measured on B200 (1M x 1M, FK metric): 2 stages / 8 rows / Q = 1 is the
+// fastest point of {2,3} x {4,8,16} x {1,2}; 72 registers and 45 KB of shared memory keep
+// 5 CTAs on an SM (more resident CTAs beat deeper rings).  The per-thread queues this
+// replaced (prefix sum, owner search, per-thread walk over parked values) cost 39.2 ms
+// against 30.4 ms.
 //
 // Reference call sites replaced: the heap loops of
 // planners/prm/pybullet/decoupled/decoupled_prm.py:484-494,531-540,947-954 and
@@ -54,11 +58,7 @@ constexpr int KNN_THREADS = KNN_CTHREADS + 32; // + producer warp
 #ifndef MMMP_KNN_STAGES
 #define MMMP_KNN_STAGES 2
 #endif
-#ifndef MMMP_KNN_DU
-#define MMMP_KNN_DU 1
-#endif
 constexpr int KNN_STAGES = MMMP_KNN_STAGES;
-constexpr int KNN_DU = MMMP_KNN_DU;            // drain: exact evaluations in flight per lane
 #ifndef MMMP_KNN_TILE
 #define MMMP_KNN_TILE 128
 #endif
@@ -79,9 +79,6 @@ constexpr int KNN_QC = KNN_RU + KNN_QSLACK;    // queue capacity per (thread, qu
 #define MMMP_KNN_WALK 2                         // producer: blocks of 16 tile boxes per side and walk step (1/2/4/8: 27.5/27.3/27.3/28.4 ms)
 #endif
 constexpr int KNN_WALK = MMMP_KNN_WALK;
-#ifndef MMMP_KNN_WARPQ
-#define MMMP_KNN_WARPQ 1                       // 1: one compacted queue per warp; 0: one queue per thread
-#endif
 constexpr float KNN_SLACK = 2.0e-5f;           // relative slack of the fp32 filter
 constexpr int KNN_CULL_MIN = 4096;             // references below which sorting does not pay
 
@@ -372,14 +369,11 @@ struct ScanCtl {                  // per-CTA control block in shared memory
     volatile float wtau[KNN_CWARPS];  // worst (largest) filter-domain bound of every consumer warp
     volatile int tile_id[KNN_STAGES];
     float tbox[KNN_STAGES][6];    // box of the tile in every stage (written by the producer with tile_id)
-#if !MMMP_KNN_WARPQ
-    int pre[KNN_CWARPS][33];      // drain: exclusive prefix of the lanes' queue lengths
-#endif
 };
 
 // shared-memory layout (floats unless noted), LS = KNN_CTHREADS * Q:
 //   ring[STAGES][ TILE*W filter | TILE*S exact ]  lv[kc][LS]  li[kc][LS]  xq[S][LS]
-//   qval[Q][QC][CTHREADS]   queue (bytes) [Q][QC][CTHREADS]   bars[2*STAGES] (u64)   ctl
+//   warp queues (u16) [CWARPS][32*Q*QC]   bars[2*STAGES] (u64)   ctl
 __host__ __device__ constexpr size_t knn_stage_floats(int W, int S) { return (size_t)KNN_TILE * (W + S); }
 __host__ __device__ constexpr size_t knn_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -396,18 +390,11 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     float* lv = ring + KNN_STAGES * stage_floats;
     int* li = reinterpret_cast<int*>(lv + (size_t)kc * LS);
     float* xq = reinterpret_cast<float*>(li + (size_t)kc * LS);
-#if MMMP_KNN_WARPQ
     // warp queues: [CWARPS][32 * Q * QC] entries of 16 bits, (query slot, owner lane) << 8 | tile row
     unsigned short* wqueue = reinterpret_cast<unsigned short*>(xq + (size_t)S * LS);
     unsigned char* queue = reinterpret_cast<unsigned char*>(wqueue);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + knn_align((size_t)(queue - smem_raw) +
                                                                       (size_t)Q * KNN_QC * KNN_CTHREADS * 2, 8));
-#else
-    float* qval = xq + (size_t)S * LS;
-    unsigned char* queue = reinterpret_cast<unsigned char*>(qval + (size_t)Q * KNN_QC * KNN_CTHREADS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + knn_align((size_t)(queue - smem_raw) +
-                                                                      (size_t)Q * KNN_QC * KNN_CTHREADS, 8));
-#endif
     ScanCtl* ctl = reinterpret_cast<ScanCtl*>(bars + 2 * KNN_STAGES);
     const uint32_t ring_s = smem_u32(ring);
     const uint32_t full_s = smem_u32(bars), empty_s = smem_u32(bars + KNN_STAGES);
@@ -602,7 +589,6 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     const int warp = tid >> 5;
     const float* tile_x = nullptr;   // exact rows of the tile being scanned
     int64_t tile_r0 = 0;
-#if MMMP_KNN_WARPQ
     constexpr int WQ_CAP = 32 * Q * KNN_QC;
     unsigned short* wq = wqueue + warp * WQ_CAP;
     int wcnt = 0;  // entries in the warp's queue (warp uniform)
@@ -697,116 +683,6 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             if (A.stats) atomicAdd(A.stats + 2, 1ull);
         }
     };
-#else
-    int qcnt[Q];
-#pragma unroll
-    for (int qq = 0; qq < Q; ++qq) qcnt[qq] = 0;
-    unsigned char* myq = queue + tid;
-
-    // Drain, per query slot: (1) the warp's queued (query, row) pairs are dealt out evenly over
-    // the 32 lanes, whichever lane queued them -- exact fp32 metric of the owner's query row
-    // (shared-memory column) against the tile's exact row (shared memory), value parked next
-    // to the queue entry; (2) every lane walks its own values and inserts the few that beat
-    // its k-th best.  Candidate order is (value, scan position): the result does not depend on
-    // visit order.
-    auto drain = [&]() {
-        const int lane = tid & 31;
-        const int wbase = warp * 32;
-        int* pre = ctl->pre[warp];
-#pragma unroll
-        for (int qq = 0; qq < Q; ++qq) {
-            const int cnt = qcnt[qq];
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;
-            if (lane == 0) pre[0] = 0;
-            pre[lane + 1] = incl;
-            __syncwarp();
-            for (int g0 = 0; g0 < total; g0 += 32 * KNN_DU) {  // KNN_DU independent pairs per lane in flight
-                float vv[KNN_DU];
-                int att[KNN_DU];
-#pragma unroll
-                for (int u = 0; u < KNN_DU; ++u) {
-                    const int g = g0 + 32 * u + lane;
-                    const int gc = g < total ? g : 0;
-                    int o = 0;  // owner lane: the largest o with pre[o] <= gc
-#pragma unroll
-                    for (int b = 16; b > 0; b >>= 1)
-                        if (pre[o + b] <= gc) o += b;
-                    const int e = gc - pre[o];
-                    const int ocol = qq * KNN_CTHREADS + wbase + o;
-                    const int at = (qq * KNN_QC + e) * KNN_CTHREADS + wbase + o;
-                    const int j = queue[at];
-                    const int64_t pos = tile_r0 + j;
-                    bool ok = pos < ref_end;
-                    if ((A.flags & 5) == 5) ok = ok && pos != q_first + ocol;  // same scan order: self = same position
-                    if (A.flags & 2) ok = ok && pos < A.query_id0 + q_first + ocol;  // causal searches keep row order
-                    const float v = exact_metric(A.M, xq + ocol, LS, tile_x + (size_t)j * S);
-                    vv[u] = ok ? v : CUDART_INF_F;
-                    att[u] = g < total ? at : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < KNN_DU; ++u)
-                    if (att[u] >= 0) qval[att[u]] = vv[u];
-            }
-            if (A.stats && lane == 0) atomicAdd(A.stats, (unsigned long long)total);
-            __syncwarp();
-            const int col = qq * KNN_CTHREADS + tid;
-            float* lvc = lv + col;
-            int* lic = li + col;
-            float tv = lvc[(kc - 1) * LS];
-            for (int e = 0; e < cnt; ++e) {
-                const int at = (qq * KNN_QC + e) * KNN_CTHREADS + tid;
-                const float v = qval[at];
-                if (!(v <= tv) || !(v < CUDART_INF_F)) continue;
-                // the list holds scan POSITIONS (ties broken by position; the scan order is
-                // deterministic): the original id is looked up once, when the list is written
-                const int64_t id = tile_r0 + queue[at];
-                if ((A.flags & 5) == 1) {  // self, found by original id (queries in their own order)
-                    const int64_t orig = A.perm ? (int64_t)__ldg(A.perm + id) : id;
-                    if (orig == A.query_id0 + qrow[qq]) continue;
-                }
-                if (v == tv && (int)id >= lic[(kc - 1) * LS]) continue;
-                int p = kc - 1;
-                while (p > 0) {
-                    const float u = lvc[(p - 1) * LS];
-                    const int ui = lic[(p - 1) * LS];
-                    if (!(u > v || (u == v && ui > (int)id))) break;
-                    lvc[p * LS] = u;
-                    lic[p * LS] = ui;
-                    --p;
-                }
-                lvc[p * LS] = v;
-                lic[p * LS] = (int)id;
-                const float tau = lvc[(kc - 1) * LS];
-                tv = tau;
-                if (tau < CUDART_INF_F) {
-                    const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
-                    thr[qq] = tf - Aq[qq];
-                    tauf[qq] = tf;
-                }
-                if (A.stats) atomicAdd(A.stats + 1, 1ull);
-            }
-            qcnt[qq] = 0;
-            __syncwarp();
-        }
-        // publish the warp's worst bound for the producer's culling test
-        float worst = 0.f;
-#pragma unroll
-        for (int k2 = 0; k2 < Q; ++k2) worst = fmaxf(worst, tauf[k2]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-        if ((tid & 31) == 0) {
-            ctl->wtau[warp] = worst;
-            if (A.stats) atomicAdd(A.stats + 2, 1ull);
-        }
-    };
-#endif
 
     for (int slot = 0;; ++slot) {
         const int s = slot % KNN_STAGES;
@@ -865,7 +741,6 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     worst = fminf(worst, m - thr[qq]);
                 }
                 // one warp-uniform branch per step
-#if MMMP_KNN_WARPQ
                 if (__any_sync(0xffffffffu, worst <= 0.f)) {
 #pragma unroll
                     for (int qq = 0; qq < Q; ++qq) {
@@ -881,32 +756,9 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     }
                     if (wcnt > WQ_CAP - 32 * Q * KNN_RU) drain();  // room for one more step
                 }
-#else
-                if (__any_sync(0xffffffffu, worst <= 0.f)) {
-                    int fill = 0;
-#pragma unroll
-                    for (int qq = 0; qq < Q; ++qq) {
-#pragma unroll
-                        for (int u = 0; u < KNN_RU; ++u)
-                            if (sv[qq][u] <= thr[qq]) {
-                                myq[(qq * KNN_QC + qcnt[qq]) * KNN_CTHREADS] = (unsigned char)(j + u);
-                                ++qcnt[qq];
-                            }
-                        fill = max(fill, qcnt[qq]);
-                    }
-                    if (__any_sync(0xffffffffu, fill > KNN_QSLACK)) drain();
-                }
-#endif
             }
             // the tile's exact rows leave with the tile: drain before releasing the slot
-#if MMMP_KNN_WARPQ
             if (wcnt) drain();
-#else
-            int pending = 0;
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq) pending |= qcnt[qq];
-            if (__any_sync(0xffffffffu, pending != 0)) drain();
-#endif
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty_s + 8 * s);
@@ -989,7 +841,7 @@ int fill_metric(const mmmp_metric* m, int ldx, MetricDev& M) {
 size_t scan_smem(int F4, int Q, int kc, int S) {
     const size_t w = F4 * 4, ls = (size_t)KNN_CTHREADS * Q;
     size_t b = (size_t)KNN_STAGES * knn_stage_floats((int)w, S) * 4 + (size_t)kc * ls * 8 + (size_t)S * ls * 4;
-    b = knn_align(b + (size_t)Q * KNN_QC * KNN_CTHREADS * (MMMP_KNN_WARPQ ? 2 : 5), 8);
+    b = knn_align(b + (size_t)Q * KNN_QC * KNN_CTHREADS * 2, 8);
     return b + 2 * KNN_STAGES * 8 + sizeof(ScanCtl) + 16;
 }
 
