@@ -86,6 +86,24 @@ def all_gather_padded(t: torch.Tensor, cap: int, size: int, group=None, fill=0) 
     return out
 
 
+def balanced_cuts(cuts, times, damping: float = 0.5):
+    """One step of the cut controller of the sharded neighbour search: `cuts` (G + 1 fractions of
+    the scan order, 0 .. 1) and the scan time every rank measured for its slice -> new cuts, moved
+    towards the widths that would have taken equal time.  Damped, because the cost per query
+    block is only locally constant.  Times that are not all positive leave the cuts alone."""
+    cuts = np.asarray(cuts, dtype=np.float64)
+    times = np.asarray(times, dtype=np.float64)
+    if times.shape[0] != cuts.shape[0] - 1 or not np.all(times > 0):
+        return cuts
+    width = np.diff(cuts)
+    want = width / times                         # slice widths that would have taken equal time
+    want /= want.sum()
+    width = (1.0 - damping) * width + damping * want
+    out = np.concatenate([[0.0], np.cumsum(width)])
+    out[-1] = 1.0
+    return out
+
+
 class RoadmapBuilder:
     def __init__(self, world: core.SpatialWorld, robot: int = 0, metric: str = "fk", k: int = 10,
                  n_steps: int = 50, step: float = 0.02, flags: int = CHECK_SELF | CHECK_OBSTACLES,
@@ -125,15 +143,7 @@ class RoadmapBuilder:
         t = torch.tensor([my_scan_ms], dtype=torch.float64, device="cuda")
         ts = [torch.empty_like(t) for _ in range(self.size)]
         dist.all_gather(ts, t, group=self.group)
-        times = np.array([float(x.item()) for x in ts])
-        if not np.all(times > 0):
-            return
-        width = np.diff(self.cuts)
-        want = width / times                         # slice widths that would have taken equal time
-        want /= want.sum()
-        width = 0.5 * width + 0.5 * want             # damped: the cost per block is only locally constant
-        self.cuts = np.concatenate([[0.0], np.cumsum(width)])
-        self.cuts[-1] = 1.0
+        self.cuts = balanced_cuts(self.cuts, np.array([float(x.item()) for x in ts]))
 
     def _mark(self, name):
         if self.timer is not None:

@@ -82,3 +82,30 @@ def test_sharding_logic_world_size_2():
     out = mgr.dict()
     mp.spawn(_worker, args=(size, _free_port(), out), nprocs=size, join=True)
     assert all(out.get(r) for r in range(size)), dict(out)
+
+
+def test_cut_controller_balances_a_skewed_scan_order():
+    """roadmap.balanced_cuts (host logic of the sharded neighbour search): with a cost per query
+    block that differs between regions of the scan order, repeated steps equalise the ranks'
+    times; equal times, bad times and a single rank leave the cuts alone; the cuts stay a
+    monotone partition of [0, 1] (what mmmp_knn_range expects)."""
+    from mmmp_b200.roadmap import balanced_cuts
+
+    def cost(lo, hi):                       # integral of a density 1 + 0.6 x over [lo, hi)
+        return (hi - lo) + 0.3 * (hi * hi - lo * lo)
+
+    for g in (2, 3, 4):
+        cuts = np.linspace(0.0, 1.0, g + 1)
+        first = np.array([cost(a, b) for a, b in zip(cuts[:-1], cuts[1:])])
+        for _ in range(12):
+            times = np.array([cost(a, b) for a, b in zip(cuts[:-1], cuts[1:])])
+            cuts = balanced_cuts(cuts, times)
+            assert cuts[0] == 0.0 and cuts[-1] == 1.0 and np.all(np.diff(cuts) > 0)
+        times = np.array([cost(a, b) for a, b in zip(cuts[:-1], cuts[1:])])
+        assert times.max() / times.min() < 1.01 < first.max() / first.min()
+        assert times.max() < first.max()
+    even = np.linspace(0.0, 1.0, 5)
+    assert np.allclose(balanced_cuts(even, np.full(4, 7.5)), even)
+    assert np.array_equal(balanced_cuts(even, np.array([1.0, 0.0, 2.0, 1.0])), even)      # a rank without a time
+    assert np.array_equal(balanced_cuts(even, np.array([1.0, 2.0])), even)                # wrong length
+    assert np.array_equal(balanced_cuts(np.array([0.0, 1.0]), np.array([3.0])), np.array([0.0, 1.0]))
