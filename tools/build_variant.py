@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """Build a tuning variant of the library with extra nvcc defines:
 
-    python tools/build_variant.py NAME -DMMMP_KNN_STAGES=3 -DMMMP_KNN_DU=1 ...
+    python tools/build_variant.py NAME -DMMMP_KNN_STAGES=3 -DMMMP_KNN_QSLACK=16 ...
 
 writes mmmp_b200/lib/variants/libmmmp_b200_NAME.so (git-ignored, travels with gpurun);
 select it at run time with MMMP_B200_LIB=<path>.
+Knobs: MMMP_KNN_{STAGES,TILE,RU,CWARPS,QSLACK,MINB,WALK,SPIN_NS} (csrc/knn_scan.cu),
+MMMP_EDGE_{LANES,DEFER_ROUNDS} (csrc/collide.cu); tools/knn_one.py prints a checksum of the answer
+so that variants can be compared for equality as well as for time.
 """
 import os
 import subprocess
