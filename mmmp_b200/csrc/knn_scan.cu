@@ -73,7 +73,11 @@ constexpr int KNN_RU = MMMP_KNN_RU;            // rows per inner-loop step
 constexpr int KNN_QSLACK = MMMP_KNN_QSLACK;    // queue entries a thread may hold before its warp drains
 constexpr int KNN_QC = KNN_RU + KNN_QSLACK;    // queue capacity per (thread, query)
 #ifndef MMMP_KNN_MINB
-#define MMMP_KNN_MINB 5                        // resident CTAs per SM the register budget must allow (72 registers)
+#define MMMP_KNN_MINB 5                        // resident CTAs per SM the register budget must allow, 4-column filter
+                                               // rows (71 registers); 8 columns: 3 CTAs, 113 registers (5 would spill 348 B)
+#endif
+#ifndef MMMP_KNN_MINB2
+#define MMMP_KNN_MINB2 3                       // the same for 8-column filter rows (joint-space L2 of a 7-DOF arm)
 #endif
 #ifndef MMMP_KNN_WALK
 #define MMMP_KNN_WALK 2                         // producer: blocks of 16 tile boxes per side and walk step (1/2/4/8: 27.5/27.3/27.3/28.4 ms)
@@ -378,7 +382,7 @@ __host__ __device__ constexpr size_t knn_stage_floats(int W, int S) { return (si
 __host__ __device__ constexpr size_t knn_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int F4, int Q>
-__global__ void __launch_bounds__(KNN_THREADS, F4 <= 2 ? MMMP_KNN_MINB : 1)
+__global__ void __launch_bounds__(KNN_THREADS, F4 == 1 ? MMMP_KNN_MINB : (F4 == 2 ? MMMP_KNN_MINB2 : 1))
 knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int W = F4 * 4;
