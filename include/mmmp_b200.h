@@ -131,9 +131,12 @@ enum {
     MMMP_CHECK_OBSTACLES = 2,   /* env.py:51-68 / planar env.py:148-205              */
     MMMP_CHECK_ROBOTS = 4,      /* env.py:70-75 / planar env.py:78-117               */
     MMMP_CHECK_BOUNDS = 8,      /* planar env.py:220-229 (ignored by spatial worlds) */
-    MMMP_CHECK_EXHAUSTIVE = 16  /* edge checks only: evaluate every interpolation step even
+    MMMP_CHECK_EXHAUSTIVE = 16, /* edge checks only: evaluate every interpolation step even
                                    when a clearance bound already proves it free (same
                                    verdicts; the cross-check of the default path)       */
+    MMMP_CHECK_NO_CAPSULES = 32 /* spatial worlds: skip the capsule stage between the links'
+                                   bounding spheres and their sphere sets (same verdicts;
+                                   the cross-check of the capsule cull)                  */
 };
 
 /* ---- (a) joint-space sampling -------------------------------------------
@@ -165,11 +168,19 @@ int mmmp_fk_chain(const mmmp_world* w, int robot, const float* q_d, int ld, int6
  * frames (frames_h[g] in 1..n_joints+1, the tip being n_joints+1), zero padded.
  * Panda.task_space_pose_distance (robots/panda.py:248-254) only depends on
  * frames 3,4,5(=6),7,8 -> 5 groups with weights 1,1,2,1,1.
- * out_filter_d (may be NULL) [N, 4] = (sum_g w_g p_g, 0): the filter row of the
- * neighbour scan (sum_g w_g |dp_g| >= |sum_g w_g dp_g|), 16-byte aligned.       */
+ * out_filter_d (may be NULL), 16-byte aligned: the filter rows of the neighbour scan.
+ *   ldfilt = 4: [N, 4] = (C, 0), C = sum_g w_g p_g the weighted centroid -- triangle
+ *               inequality: sum_g w_g |dp_g| >= |dC|;
+ *   ldfilt = 8: [N, 8] = (C, D, 0, 0) "dual rows": with A = the weighted sum over the first
+ *               floor(n/2) groups and B over the rest, C = A + B and D = A - B.  Both
+ *               |dC| <= m and |dA|^2 + |dB|^2 = (|dC|^2 + |dD|^2) / 2 <= (|dA| + |dB|)^2 <= m^2
+ *               hold for the metric value m, and the pair of tests passes ~4x fewer
+ *               candidates than the centroid alone (the halves of the chain move apart
+ *               long before their sum does).  mmmp_knn recognises these rows by
+ *               kind = GROUP_L2_SUM, ldf = 8, fdim = 6.                              */
 int mmmp_fk_features(const mmmp_world* w, int robot, const float* q_d, int ld, int64_t N,
                      const int32_t* frames_h, const float* weights_h, int n_frames,
-                     float* out_d, int ldf, float* out_filter_d, void* stream);
+                     float* out_d, int ldf, float* out_filter_d, int ldfilt, void* stream);
 /* frame groups of the FK metric for mmmp_fk_features / mmmp_metric: frames whose
  * origin depends on q, coincident consecutive frames merged with multiplicity as
  * weight.  frames_h / weights_h hold MMMP_MAX_GROUPS entries.                 */
@@ -185,7 +196,9 @@ int mmmp_planar_fk(const mmmp_world* w, int arm, const double* q_d, int ld, int6
 
 /* ---- (c) collision checks -----------------------------------------------
  * Spatial worlds: sphere decomposition of every link against obstacle
- * primitives, the robot's own non-adjacent links and other robots' links;
+ * primitives, the robot's own non-adjacent links and other robots' links,
+ * culled link by link with a bounding sphere and then a bounding CAPSULE
+ * (fitted at world creation around the link's spheres: conservative);
  * replaces pybullet getClosestPoints(distance=0) at
  * planners/prm/pybullet/env.py:65,72,81 as composed by
  * DecoupledPRM.is_collision_free_sample (decoupled_prm.py:840-850) and
@@ -264,7 +277,9 @@ typedef struct mmmp_metric {
  * xref_d/xquery_d [., ldx] on which metric_h is evaluated for the pairs that
  * pass.  L2 / SQ_SUM: pass the same rows for both (fdim = metric.dim).
  * GROUP_L2_SUM: exact rows = mmmp_fk_features out_d, filter rows = its
- * out_filter_d (ldf 4, fdim 3).  n_ref < 2^28.                              */
+ * out_filter_d: centroid rows (ldf 4, fdim 3) or dual rows (ldf 8, fdim 6: the first
+ * three columns bound the metric m by |d|^2 <= m^2, all six by |d|^2 <= 2 m^2; both
+ * tests run in the hot loop, tiles are culled on the first three).  n_ref < 2^28.  */
 int mmmp_knn(const float* fref_d, const float* xref_d, int64_t n_ref,
              const float* fquery_d, const float* xquery_d, int64_t n_query,
              int ldf, int fdim, int ldx, const mmmp_metric* metric_h, int k,
@@ -293,6 +308,19 @@ int mmmp_knn_range(const float* fref_d, const float* xref_d, int64_t n_ref, int 
                    int ldx, const mmmp_metric* metric, int k, int exclude_self, double frac_lo,
                    double frac_hi, int32_t* out_rows_d, int64_t* n_rows_h, int32_t* out_idx_d,
                    float* out_dist_d, void* stream);
+
+/* Post-search exchange of a sharded search ("the local adjacency lists are gathered
+ * afterwards"): the m rows a rank answered (out_rows_d of mmmp_knn_range, re-ranked by
+ * mmmp_knn_refine) packed as records of 2 + 3k 32-bit words [row id, ambiguous, idx[k],
+ * dist[k] fp64] in rec_d [cap, 2 + 3k] (records m..cap-1: row id -1), so that one all-gather
+ * of equal blocks ships them; mmmp_scatter_neighbour_records writes any number of gathered
+ * records into tables in the caller's row order (idx_d [n, k], dist_d [n, k] or NULL,
+ * amb_d [n] or NULL), skipping row ids outside [0, n).                              */
+int mmmp_pack_neighbour_records(const int32_t* rows_d, const int32_t* idx_d, const double* dist_d,
+                                const uint8_t* amb_d, int64_t m, int k, int64_t cap, void* rec_d,
+                                void* stream);
+int mmmp_scatter_neighbour_records(const void* rec_d, int64_t n_records, int k, int64_t n,
+                                   int32_t* idx_d, double* dist_d, uint8_t* amb_d, void* stream);
 
 /* profiling aid: enable != 0 turns on five device counters of the scan kernel
  * (exact evaluations, list insertions, warp drains, tiles loaded, most tiles
@@ -358,6 +386,23 @@ int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, const double* q
                                  double* nbr_dist_h, uint8_t* edge_free_h,
                                  float* timings_ms_h);
 
+/* The same call up to the ROADMAP: candidates as above with k = k1, then the greedy
+ * degree-capped accept pass (connect_nearest_neighbors_degree decoupled_prm.py:496-503,
+ * mmmp_greedy_degree_connect_device) and the connected components of the result
+ * (decoupled_prm.py:613-636).  Additional host outputs, sized for N rows: adj_h [N, k2]
+ * int32 node ids (-1 padded, the reference's list order), deg_h [N], labels_h [N] (may be
+ * NULL; smallest node id of the component), n_components_h (may be NULL).  The neighbour
+ * tables travel device->host on a second stream while the edges are checked, the verdicts
+ * while the accept pass runs (page-locked host buffers make the overlap real).
+ * timings_ms_h (may be NULL) [10]: h2d, accept test + compaction, features, scan, re-rank,
+ * edge collision, d2h tail after the last kernel, total, accept pass, components.           */
+int mmmp_roadmap_build_host(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D,
+                            int metric_kind, int k1, int k2, int n_steps, double step,
+                            uint32_t flags, int64_t* n_nodes_h, int32_t* node_src_h,
+                            int32_t* nbr_idx_h, double* nbr_dist_h, uint8_t* edge_free_h,
+                            int32_t* adj_h, int32_t* deg_h, int32_t* labels_h,
+                            int64_t* n_components_h, float* timings_ms_h);
+
 /* edges_d[e] = (e / k, nbr_d[e]) for a flat [n, k] neighbour table            */
 int mmmp_edges_from_knn(const int32_t* nbr_d, int64_t n, int k, int32_t* edges_d,
                         void* stream);
@@ -370,6 +415,19 @@ int mmmp_edges_from_knn(const int32_t* nbr_d, int64_t n, int k, int32_t* edges_d
 int mmmp_greedy_degree_connect(const int32_t* nbr_idx_h, const uint8_t* edge_free_h,
                                int64_t N, int k1, int k2, int cap, int32_t* adj_h,
                                int32_t* deg_h);
+
+/* The same pass on the GPU, device tables in, device tables out (asynchronous on `stream`):
+ * identical adjacency -- the same edges in the same order inside every list -- computed in a
+ * few data-parallel rounds instead of one sequential sweep (csrc/greedy.cu: every node
+ * bounds its degree at the time of each candidate from the decisions known so far; a
+ * candidate is accepted once the cap provably cannot bind at either end, rejected once it
+ * provably binds at one).  nbr_idx_d [N, k1], edge_free_d [N, k1] as produced by the
+ * neighbour search and mmmp_collide_edges; adj_d [N, cap] (-1 padded), deg_d [N];
+ * rounds_d (may be NULL): device scalar receiving the number of rounds.
+ * N * k1 < 2^31.  This is what puts "roadmap build" on the device up to the adjacency.  */
+int mmmp_greedy_degree_connect_device(const int32_t* nbr_idx_d, const uint8_t* edge_free_d,
+                                      int64_t N, int k1, int k2, int cap, int32_t* adj_d,
+                                      int32_t* deg_d, int32_t* rounds_d, void* stream);
 
 /* Connected components of a roadmap: the partition computed by
  * compute_connected_components (decoupled_prm.py:613-636).  adj_d [N, cap]

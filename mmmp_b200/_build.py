@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmmmp_b200.so")
-SOURCES = ["world.cu", "sample.cu", "fk.cu", "collide.cu", "planar.cu", "knn_scan.cu", "knn.cu", "components.cu",
+SOURCES = ["world.cu", "sample.cu", "fk.cu", "collide.cu", "planar.cu", "knn_scan.cu", "knn.cu", "components.cu", "greedy.cu",
            "ik.cu", "host_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

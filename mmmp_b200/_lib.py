@@ -21,7 +21,7 @@ MAX_GROUPS = 8
 
 OBS_PLANE, OBS_SPHERE, OBS_BOX, OBS_CYLINDER = 0, 1, 2, 3
 POBS_RECT, POBS_CIRCLE = 0, 1
-CHECK_SELF, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_BOUNDS, CHECK_EXHAUSTIVE = 1, 2, 4, 8, 16
+CHECK_SELF, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_BOUNDS, CHECK_EXHAUSTIVE, CHECK_NO_CAPSULES = 1, 2, 4, 8, 16, 32
 METRIC_L2, METRIC_GROUP_L2_SUM, METRIC_SQ_SUM = 0, 1, 2
 
 
@@ -101,7 +101,7 @@ SIGNATURES = {
     "mmmp_sample_uniform": [_P, _P, _I, _I64, _U64, _U64, _I, _P, _I, _P, _I, _P],
     "mmmp_pack_f32": [_P, _I, _I, _I64, _P, _I, _P],
     "mmmp_fk_chain": [_P, _I, _P, _I, _I64, _P, _P, _P],
-    "mmmp_fk_features": [_P, _I, _P, _I, _I64, _P, _P, _I, _P, _I, _P, _P],
+    "mmmp_fk_features": [_P, _I, _P, _I, _I64, _P, _P, _I, _P, _I, _P, _I, _P],
     "mmmp_fk_metric_groups": [_P, _I, _P, _P, _P],
     "mmmp_fk_chain_f64": [_P, _I, _P, _I, _I64, _P, _P],
     "mmmp_planar_fk": [_P, _I, _P, _I, _I64, _P, _P],
@@ -114,6 +114,8 @@ SIGNATURES = {
     "mmmp_knn": [_P, _P, _I64, _P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _I, _I64, _P, _P, _P],
     "mmmp_knn_shard": [_P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "mmmp_knn_range": [_P, _P, _I64, _I, _I, _I, C.POINTER(Metric), _I, _I, _D, _D, _P, _P, _P, _P, _P],
+    "mmmp_pack_neighbour_records": [_P, _P, _P, _P, _I64, _I, _I64, _P, _P],
+    "mmmp_scatter_neighbour_records": [_P, _I64, _I, _I64, _P, _P, _P, _P],
     "mmmp_knn_stats": [_I, _P],
     "mmmp_edge_stats": [_I, _P],
     "mmmp_knn_refine": [_P, _P, _I, C.POINTER(Metric), _P, _P, _I64, _I, _I, _D, _P, _P, _P, _P],
@@ -122,7 +124,9 @@ SIGNATURES = {
     "mmmp_exclusive_scan_i32": [_P, _I64, _P, _P],
     "mmmp_edges_from_knn": [_P, _I64, _I, _P, _P],
     "mmmp_roadmap_candidates_host": [_P, _I, _P, _I64, _I, _I, _I, _I, _D, _U32, _P, _P, _P, _P, _P, _P],
+    "mmmp_roadmap_build_host": [_P, _I, _P, _I64, _I, _I, _I, _I, _I, _D, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "mmmp_greedy_degree_connect": [_P, _P, _I64, _I, _I, _I, _P, _P],
+    "mmmp_greedy_degree_connect_device": [_P, _P, _I64, _I, _I, _I, _P, _P, _P, _P],
     "mmmp_version": [],
     "mmmp_device_info": [_P, _P, _P, _P],
     "mmmp_connected_components": [_P, _P, _I64, _I, _P, _P, _P],

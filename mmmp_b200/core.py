@@ -389,6 +389,28 @@ def knn_refine(ref64: torch.Tensor, query64: torch.Tensor, metric64: Metric, can
     return idx, dist, amb
 
 
+def pack_neighbour_records(rows: torch.Tensor, idx: torch.Tensor, dist: torch.Tensor, amb: Optional[torch.Tensor],
+                           cap: int) -> torch.Tensor:
+    """Rows answered by a sharded search as records [cap, 2 + 3k] int32 (row id, ambiguous, idx,
+    dist as fp64 bit pairs; padding records carry row id -1): one all-gather ships them."""
+    m, k = idx.shape
+    rec = torch.empty((cap, 2 + 3 * k), dtype=torch.int32, device=idx.device)
+    _lib.call("mmmp_pack_neighbour_records", _ptr(_dev(rows, torch.int32)), _ptr(_dev(idx, torch.int32)),
+              _ptr(_dev(dist, torch.float64)), _ptr(amb), m, k, cap, _ptr(rec), _stream())
+    return rec
+
+
+def scatter_neighbour_records(rec: torch.Tensor, k: int, n: int, want_dist: bool = True):
+    """Gathered records -> (idx [n, k] int32, dist [n, k] fp64 or None, amb [n] u8) in row order."""
+    rec = _dev(rec, torch.int32)
+    idx = torch.empty((n, k), dtype=torch.int32, device=rec.device)
+    dist = torch.empty((n, k), dtype=torch.float64, device=rec.device) if want_dist else None
+    amb = torch.empty((n,), dtype=torch.uint8, device=rec.device)
+    _lib.call("mmmp_scatter_neighbour_records", _ptr(rec), rec.shape[0], k, n, _ptr(idx), _ptr(dist), _ptr(amb),
+              _stream())
+    return idx, dist, amb
+
+
 def knn_exact(ref: Features, query: Features, k: int, pad: int = 6, exclude_self: bool = True,
               causal: bool = False, query_id0: int = 0):
     """scan with k+pad candidates, then fp64 re-rank -> (idx, dist64, ambiguous)."""
@@ -431,10 +453,30 @@ def greedy_degree_connect(nbr_idx: np.ndarray, edge_free: np.ndarray, k2: int, c
     return adj, deg
 
 
-def connected_components(adj: torch.Tensor, mask: Optional[torch.Tensor] = None):
+def greedy_degree_connect_device(nbr_idx: torch.Tensor, edge_free: torch.Tensor, k2: int, cap: Optional[int] = None,
+                                 return_rounds: bool = False):
+    """connect_nearest_neighbors_degree's accept pass (decoupled_prm.py:496-503) on the GPU:
+    device tables in, (adj [N, cap] int32 -1 padded, deg [N] int32) out, identical to the
+    sequential replay (mmmp_greedy_degree_connect), list order included."""
+    nbr_idx = _dev(nbr_idx, torch.int32)
+    edge_free = _dev(edge_free, torch.uint8)
+    N, k1 = nbr_idx.shape
+    if tuple(edge_free.shape) != (N, k1):
+        raise MmmpError("greedy_degree_connect_device: edge_free must have the shape of nbr_idx")
+    cap = k2 if cap is None else cap
+    adj = torch.empty((N, cap), dtype=torch.int32, device=nbr_idx.device)
+    deg = torch.empty((N,), dtype=torch.int32, device=nbr_idx.device)
+    rounds = torch.zeros((1,), dtype=torch.int32, device=nbr_idx.device) if return_rounds else None
+    _lib.call("mmmp_greedy_degree_connect_device", _ptr(nbr_idx), _ptr(edge_free), N, k1, k2, cap, _ptr(adj), _ptr(deg),
+              _ptr(rounds), _stream())
+    return (adj, deg, int(rounds.item())) if return_rounds else (adj, deg)
+
+
+def connected_components(adj: torch.Tensor, mask: Optional[torch.Tensor] = None, sync: bool = True):
     """Partition of compute_connected_components (decoupled_prm.py:613-636) on the GPU.
     adj [N, cap] int32 neighbour table (-1 padded), mask [N, cap] uint8 (1 = edge present) or None.
-    -> (labels [N] int32: smallest node id of the node's component, number of components)."""
+    -> (labels [N] int32: smallest node id of the node's component, number of components);
+    sync=False leaves the count on the device (a [1] int64 tensor) and does not wait for the stream."""
     dev = _require_cuda()
     adj = _dev(adj, torch.int32)
     n, cap = adj.shape
@@ -446,7 +488,7 @@ def connected_components(adj: torch.Tensor, mask: Optional[torch.Tensor] = None)
     count = torch.zeros((1,), dtype=torch.int64, device=dev)
     _lib.call("mmmp_connected_components", _ptr(adj), _ptr(mask) if mask is not None else None, n, cap, _ptr(labels),
               _ptr(count), _stream())
-    return labels, int(count.item())
+    return labels, (int(count.item()) if sync else count)
 
 
 def launch_count() -> int:
@@ -580,26 +622,29 @@ class SpatialWorld(_World):
         _lib.call("mmmp_fk_metric_groups", self.handle, robot, frames, weights, C.byref(n))
         return list(frames[: n.value]), list(weights[: n.value])
 
-    def fk_features(self, q64: torch.Tensor, q32: Optional[torch.Tensor] = None, robot: int = 0) -> Features:
+    def fk_features(self, q64: torch.Tensor, q32: Optional[torch.Tensor] = None, robot: int = 0,
+                    dual: bool = True) -> Features:
         """Row sets of the FK metric (Panda.task_space_pose_distance, robots/panda.py:248-254):
         exact fp32 rows = xyz of the q-dependent frames (coincident frames merged, weights =
-        multiplicity), filter rows = their weighted centroid, fp64 rows = all frame positions."""
+        multiplicity), filter rows = dual rows (centroid + half-chain difference, see
+        mmmp_fk_features; dual=False: the centroid alone), fp64 rows = all frame positions."""
         q64 = _dev(q64, torch.float64)
         q32 = pack_f32(q64) if q32 is None else _dev(q32, torch.float32)
         frames, weights = self.metric_groups(robot)
         ldf = pad4(3 * len(frames))
         n = q32.shape[0]
         out = torch.empty((n, ldf), dtype=torch.float32, device=q32.device)
-        filt = torch.empty((n, 4), dtype=torch.float32, device=q32.device)
+        ldfilt = 8 if dual else 4
+        filt = torch.empty((n, ldfilt), dtype=torch.float32, device=q32.device)
         fr = (C.c_int32 * len(frames))(*frames)
         wt = (C.c_float * len(frames))(*weights)
         _lib.call("mmmp_fk_features", self.handle, robot, _ptr(q32), q32.shape[1], n, fr, wt, len(frames),
-                  _ptr(out), ldf, _ptr(filt), _stream())
+                  _ptr(out), ldf, _ptr(filt), ldfilt, _stream())
         L = self.robots[robot].model["n_joints"] + 1
         pos64 = self.fk64(q64, robot).reshape(n, 3 * L)
         m32 = make_metric(METRIC_GROUP_L2_SUM, 3 * len(frames), weights)
         m64 = make_metric(METRIC_GROUP_L2_SUM, 3 * L, [1.0] * L)
-        return Features(filt, out, pos64, m32, m64, 3)
+        return Features(filt, out, pos64, m32, m64, 6 if dual else 3)
 
     def collide_robot_pairs(self, qa: torch.Tensor, qb: torch.Tensor, ra: int, rb: int):
         qa, qb = _dev(qa, torch.float32), _dev(qb, torch.float32)
@@ -632,6 +677,38 @@ class SpatialWorld(_World):
         n = n_nodes.value
         return {"n_nodes": n, "node_src": node_src[:n], "nbr_idx": nbr[:n], "nbr_dist": dist[:n],
                 "edge_free": free[:n], "timings_ms": timings}
+
+
+    def roadmap_build_host(self, q64: np.ndarray, robot: int, metric_kind: int, k1: int, k2: int, n_steps: int,
+                           step: float, flags: int = CHECK_SELF | CHECK_OBSTACLES, out: Optional[dict] = None):
+        """Host arrays in, the ROADMAP out (mmmp_roadmap_build_host): candidate tables as
+        roadmap_candidates_host plus adj [n, k2], deg [n], labels [n], n_components.
+        `out` = host_buffers(N, k1, k2) re-uses page-locked output buffers across calls."""
+        q64 = np.ascontiguousarray(q64, dtype=np.float64)
+        N, D = q64.shape
+        b = host_buffers(N, k1, k2) if out is None else out
+        if b["nbr_idx"].shape[0] < N or b["nbr_idx"].shape[1] != k1 or b["adj"].shape[1] != k2:
+            raise MmmpError("roadmap_build_host: output buffers do not fit this call")
+        n_nodes, n_comp = C.c_int64(0), C.c_int64(0)
+        timings = np.zeros((10,), dtype=np.float32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.call("mmmp_roadmap_build_host", self.handle, robot, vp(q64), N, D, metric_kind, k1, k2, n_steps,
+                  C.c_double(step), flags, C.byref(n_nodes), vp(b["node_src"]), vp(b["nbr_idx"]), vp(b["nbr_dist"]),
+                  vp(b["edge_free"]), vp(b["adj"]), vp(b["deg"]), vp(b["labels"]), C.byref(n_comp), vp(timings))
+        n = n_nodes.value
+        res = {key: b[key][:n] for key in ("node_src", "nbr_idx", "nbr_dist", "edge_free", "adj", "deg", "labels")}
+        res.update(n_nodes=n, n_components=n_comp.value, timings_ms=timings)
+        return res
+
+
+def host_buffers(N: int, k1: int, k2: int, pinned: bool = True) -> dict:
+    """Output buffers of SpatialWorld.roadmap_build_host for up to N samples (page-locked by default:
+    the library's device-to-host copies then overlap its kernels)."""
+    def host(shape, t_dtype):
+        return torch.empty(shape, dtype=t_dtype, pin_memory=pinned and torch.cuda.is_available()).numpy()
+    return {"node_src": host((N,), torch.int32), "nbr_idx": host((N, k1), torch.int32),
+            "nbr_dist": host((N, k1), torch.float64), "edge_free": host((N, k1), torch.uint8),
+            "adj": host((N, k2), torch.int32), "deg": host((N,), torch.int32), "labels": host((N,), torch.int32)}
 
 
 class PlanarWorld(_World):

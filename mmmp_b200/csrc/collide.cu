@@ -201,6 +201,64 @@ __device__ __forceinline__ bool link_pair_hit(const RobotDev& RA, int la, const 
     return false;
 }
 
+// Squared distance between the axes of the bounding capsules of link la (pose TA) and link lb (pose
+// TB), and the sum of their radii.  The closest pair of points is found in fp32 (Ericson's segment /
+// segment clamp sequence); whatever rounding does to the parameters, the value is a distance between
+// two points that DO lie on the segments, so it can exceed the true minimum only by the (second
+// order) effect of the parameter error -- callers keep a 0.1 mm margin.
+__device__ __forceinline__ void capsule_pair(const RobotDev& RA, int la, const Affine& TA, const RobotDev& RB, int lb,
+                                             const Affine& TB, float& d2, float& rr) {
+    const float4 a0 = RA.cap_a[la], a1 = RA.cap_b[la], b0 = RB.cap_a[lb], b1 = RB.cap_b[lb];
+    const float3 p1 = affine_point(TA, a0.x, a0.y, a0.z), q1 = affine_point(TA, a1.x, a1.y, a1.z);
+    const float3 p2 = affine_point(TB, b0.x, b0.y, b0.z), q2 = affine_point(TB, b1.x, b1.y, b1.z);
+    const float d1x = q1.x - p1.x, d1y = q1.y - p1.y, d1z = q1.z - p1.z;
+    const float d2x = q2.x - p2.x, d2y = q2.y - p2.y, d2z = q2.z - p2.z;
+    const float rx = p1.x - p2.x, ry = p1.y - p2.y, rz = p1.z - p2.z;
+    const float a = fmaf(d1x, d1x, fmaf(d1y, d1y, d1z * d1z)), e = fmaf(d2x, d2x, fmaf(d2y, d2y, d2z * d2z));
+    const float f = fmaf(d2x, rx, fmaf(d2y, ry, d2z * rz)), c = fmaf(d1x, rx, fmaf(d1y, ry, d1z * rz));
+    const float b = fmaf(d1x, d2x, fmaf(d1y, d2y, d1z * d2z));
+    const float denom = fmaf(a, e, -b * b);
+    const float inv_a = __fdividef(1.f, fmaxf(a, 1e-20f)), inv_e = __fdividef(1.f, fmaxf(e, 1e-20f));
+    float sp = denom > 1e-7f * a * e ? __saturatef(__fdividef(fmaf(b, f, -c * e), denom)) : 0.f;
+    float tp = fmaf(b, sp, f) * inv_e;
+    if (tp < 0.f) {
+        tp = 0.f;
+        sp = __saturatef(-c * inv_a);
+    } else if (tp > 1.f) {
+        tp = 1.f;
+        sp = __saturatef((b - c) * inv_a);
+    }
+    const float ex = fmaf(sp, d1x, rx) - tp * d2x, ey = fmaf(sp, d1y, ry) - tp * d2y, ez = fmaf(sp, d1z, rz) - tp * d2z;
+    d2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+    rr = a0.w + b0.w;
+}
+
+#define MMMP_CAPSULE_MARGIN 1.0e-4f   // metres kept in hand when a capsule test skips a descent
+
+// Link pair whose bounding spheres overlap (GAP: are closer than `want`): capsule against capsule
+// first; only if that cannot separate them either (GAP: cannot prove `want`) are the spheres of the
+// two links tested.  Returns true on a collision; GAP: g = clearance proven for the pair.
+template <bool GAP>
+__device__ __forceinline__ bool link_pair_refine(const RobotDev& RA, int la, const Affine& TA, const RobotDev& RB, int lb,
+                                                 const Affine& TB, bool capsules, float want, float& g) {
+    if (capsules && RA.cap_a[la].w >= 0.f && RB.cap_a[lb].w >= 0.f) {
+        float d2, rr;
+        capsule_pair(RA, la, TA, RB, lb, TB, d2, rr);
+        if (GAP) {
+            const float gc = fast_sqrt(d2) - rr - MMMP_CAPSULE_MARGIN;
+            if (gc > want) {
+                g = fmaxf(g, gc);
+                return false;
+            }
+        } else {
+            const float lim = rr + MMMP_CAPSULE_MARGIN;
+            if (d2 > lim * lim) return false;
+        }
+    }
+    g = __int_as_float(0x7f800000);
+    return link_pair_hit<GAP>(RA, la, TA, RB, lb, TB, want, g);
+}
+
 // bit of the pair table P at joint values (qu, qw); no branch, so that look-ups of several
 // steps can be in flight together
 __device__ __forceinline__ unsigned table_bit(const WorldDev* __restrict__ Wg, const PairTableDev& P, float qu,
@@ -241,6 +299,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
     const int n_r = hdr->n_r;
     const int mode = hdr->mode;
     const int n_obs = (flags & MMMP_CHECK_OBSTACLES) ? hdr->n_obs : 0;
+    const bool capsules = !(flags & MMMP_CHECK_NO_CAPSULES);
     float* cen = fr + (size_t)hdr->slots * 12 * stride;
     float* vel = cen + (size_t)hdr->links * 3 * stride;
     float tsafe = INF;
@@ -351,8 +410,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                     Affine TA, TB;
                     load_frame(TA, fr, stride, slot0, R.frame_store[mode][fa]);
                     load_frame(TB, fr, stride, slot0, R.frame_store[mode][fb]);
-                    g = INF;
-                    if (link_pair_hit<GAP>(R, pr.x, TA, R, pr.y, TB, want, g)) return HIT;
+                    if (link_pair_refine<GAP>(R, pr.x, TA, R, pr.y, TB, capsules, want, g)) return HIT;
                 }
                 if (GAP) tsafe = fminf(tsafe, __fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)));
             }
@@ -394,8 +452,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                             Affine TA, TB;
                             load_frame(TA, fr, stride, hdr->frame_slot[l1], R1.frame_store[mode][fa]);
                             load_frame(TB, fr, stride, hdr->frame_slot[l2], R2.frame_store[mode][fb]);
-                            g = INF;
-                            if (link_pair_hit<GAP>(R1, la, TA, R2, lb, TB, want, g)) return HIT;
+                            if (link_pair_refine<GAP>(R1, la, TA, R2, lb, TB, capsules, want, g)) return HIT;
                         }
                         if (GAP) tsafe = fminf(tsafe, __fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)));
                     }

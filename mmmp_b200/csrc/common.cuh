@@ -45,6 +45,11 @@ struct RobotDev {
     float base[12];
     float origin[MMMP_MAX_JOINTS + 1][12];
     float4 link_bound[MMMP_MAX_LINKS];  // bounding sphere, frame local (frame-0 links: WORLD)
+    // bounding CAPSULE of every link's spheres (fitted at world creation, contains them all): segment
+    // cap_a.xyz -- cap_b.xyz in the link's frame (frame-0 links: WORLD), radius cap_a.w (< 0: none).
+    // Link pairs whose bounding spheres overlap are tested capsule against capsule before anybody
+    // descends to the sphere level (the links are elongated: the capsules are 2-3x tighter).
+    float4 cap_a[MMMP_MAX_LINKS], cap_b[MMMP_MAX_LINKS];
     int link_frame[MMMP_MAX_LINKS];              // non-decreasing in the link id
     int frame_link_begin[MMMP_MAX_JOINTS + 2];   // links of frame f: [begin[f], begin[f+1])
     int link_sphere_begin[MMMP_MAX_LINKS + 1];

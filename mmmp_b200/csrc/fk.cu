@@ -67,10 +67,11 @@ struct FrameSel {
 };
 
 // FK-metric feature rows: xyz of the selected frames, zero padded to ldf; and the filter
-// row of the neighbour scan: the weighted centroid sum_g w_g p_g (xyz, 0)
+// row of the neighbour scan: the weighted centroid sum_g w_g p_g (xyz, 0); dual rows: see
+// mmmp_fk_features in include/mmmp_b200.h
 __global__ void __launch_bounds__(256)
 fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __restrict__ q, int ld, int64_t N,
-                   FrameSel sel, float* __restrict__ out, int ldf, float4* __restrict__ out_filter) {
+                   FrameSel sel, float* __restrict__ out, int ldf, float4* __restrict__ out_filter, int dual) {
     __shared__ ChainSmem C;
     {
         const RobotDev& R = W->robots[robot];
@@ -86,7 +87,8 @@ fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __res
         affine_load(T, C.base);
         const float* qi = q + i * ld;
         float* o = out + i * ldf;
-        float cx = 0.f, cy = 0.f, cz = 0.f;
+        float cx = 0.f, cy = 0.f, cz = 0.f;   // weighted sum over ALL groups
+        float ax = 0.f, ay = 0.f, az = 0.f;   // ... over the first floor(n / 2) groups
         for (int j = 0; j <= n; ++j) {
             if (j < n) {
                 float s, c;
@@ -103,10 +105,20 @@ fk_features_kernel(const WorldDev* __restrict__ W, int robot, const float* __res
                     cx = fmaf(sel.weight[g], T.m[3], cx);
                     cy = fmaf(sel.weight[g], T.m[7], cy);
                     cz = fmaf(sel.weight[g], T.m[11], cz);
+                    if (g < sel.n / 2) {
+                        ax = fmaf(sel.weight[g], T.m[3], ax);
+                        ay = fmaf(sel.weight[g], T.m[7], ay);
+                        az = fmaf(sel.weight[g], T.m[11], az);
+                    }
                 }
         }
         for (int c = 3 * sel.n; c < ldf; ++c) o[c] = 0.f;
-        if (out_filter) out_filter[i] = make_float4(cx, cy, cz, 0.f);
+        if (out_filter && !dual) out_filter[i] = make_float4(cx, cy, cz, 0.f);
+        if (out_filter && dual) {  // C = A + B (the centroid), D = A - B = 2 A - C
+            const float dx = 2.f * ax - cx, dy = 2.f * ay - cy, dz = 2.f * az - cz;
+            out_filter[2 * i] = make_float4(cx, cy, cz, dx);
+            out_filter[2 * i + 1] = make_float4(dy, dz, 0.f, 0.f);
+        }
     }
 }
 
@@ -191,7 +203,7 @@ extern "C" int mmmp_fk_chain_f64(const mmmp_world* w, int robot, const double* q
 
 extern "C" int mmmp_fk_features(const mmmp_world* w, int robot, const float* q, int ld, int64_t N,
                                 const int32_t* frames, const float* weights, int n_frames, float* out, int ldf,
-                                float* out_filter, void* stream) {
+                                float* out_filter, int ldfilt, void* stream) {
     if (!w || !q || !out || !frames || N < 0) return MMMP_ERR_ARG;
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
@@ -207,10 +219,10 @@ extern "C" int mmmp_fk_features(const mmmp_world* w, int robot, const float* q, 
         sel.frame[g] = frames[g];
         sel.weight[g] = weights ? weights[g] : 1.f;
     }
-    if (out_filter && (((uintptr_t)out_filter) & 15)) return MMMP_ERR_ARG;
+    if (out_filter && ((((uintptr_t)out_filter) & 15) || (ldfilt != 4 && ldfilt != 8))) return MMMP_ERR_ARG;
     if (N == 0) return MMMP_OK;
     MMMP_LAUNCH(fk_features_kernel, fk_grid(N, 256), 256, 0, stream, w->spatial_d, robot, q, ld, N, sel, out, ldf,
-                reinterpret_cast<float4*>(out_filter));
+                reinterpret_cast<float4*>(out_filter), ldfilt == 8 ? 1 : 0);
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }

@@ -98,13 +98,27 @@ extern "C" int mmmp_fk_metric_groups(const mmmp_world* w, int robot, int32_t* fr
     return MMMP_OK;
 }
 
-extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D,
-                                            int metric_kind, int k, int n_steps, double step, uint32_t flags,
-                                            int64_t* n_nodes_h, int32_t* node_src_h, int32_t* nbr_idx_h,
-                                            double* nbr_dist_h, uint8_t* edge_free_h, float* timings_ms_h) {
+extern "C" int mmmp_greedy_degree_connect_device(const int32_t* nbr_idx_d, const uint8_t* edge_free_d, int64_t N,
+                                                 int k1, int k2, int cap, int32_t* adj_d, int32_t* deg_d,
+                                                 int32_t* rounds_d, void* stream);
+extern "C" int mmmp_connected_components(const int32_t* adj_d, const uint8_t* mask_d, int64_t N, int cap,
+                                         int32_t* labels_d, int64_t* n_components_d, void* stream);
+
+// k2 > 0: also the accepted adjacency (greedy degree pass) and its components
+static int roadmap_host_impl(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D, int metric_kind,
+                             int k, int n_steps, double step, uint32_t flags, int k2, int64_t* n_nodes_h,
+                             int32_t* node_src_h, int32_t* nbr_idx_h, double* nbr_dist_h, uint8_t* edge_free_h,
+                             int32_t* adj_h, int32_t* deg_h, int32_t* labels_h, int64_t* n_components_h,
+                             float* timings_ms_h) {
     if (!w || !q64_h || !n_nodes_h || !node_src_h || !nbr_idx_h || !edge_free_h) return MMMP_ERR_ARG;
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (N < 1 || D < 1 || k < 1 || k > MMMP_MAX_K) return MMMP_ERR_ARG;
+    if (k2 < 0 || (k2 > 0 && (!adj_h || !deg_h))) return MMMP_ERR_ARG;
+    {
+        int cur = -1;
+        MMMP_CUDA_TRY(cudaGetDevice(&cur));
+        if (cur != w->device) return MMMP_ERR_ARG;   // the world's tables live on another device
+    }
     if (robot < 0 || robot >= w->spatial_h->n_robots) return MMMP_ERR_ARG;
     const int nj = w->spatial_h->robots[robot].n_joints;
     if (D != nj) return MMMP_ERR_ARG;
@@ -118,15 +132,22 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
     if (kc > MMMP_MAX_K) kc = MMMP_MAX_K;
 
     mmmp_pool_keep();
-    cudaStream_t s;
+    cudaStream_t s, s2;   // s: compute; s2: device-to-host copies that overlap the next stage
     MMMP_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e2 = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    if (e2 != cudaSuccess) {
+        cudaStreamDestroy(s);
+        return MMMP_ERR_CUDA_BASE + (int)e2;
+    }
     tl_alloc_stream = s;
-    cudaEvent_t ev[9];
+    cudaEvent_t ev[11], ready;
     for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
     int rc = MMMP_OK;
     int64_t n_nodes = 0;
     {
-        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, edges, ecoll, amb;
+        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, edges, ecoll, amb, adj,
+            deg, labels, ncomp;
         const int L = nj + 1;
         auto T = [&](cudaError_t e) {
             if (e != cudaSuccess && rc == MMMP_OK) rc = MMMP_ERR_CUDA_BASE + (int)e;
@@ -198,11 +219,11 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                     T(feat.alloc(sizeof(float) * n * ldf));
                     T(pos64.alloc(sizeof(double) * n * 3 * L));
                     if (rc == MMMP_OK) {
-                        T(filt.alloc(sizeof(float) * n * 4));
+                        T(filt.alloc(sizeof(float) * n * 8));
                         R(mmmp_fk_features(w, robot, nq32.as<float>(), ld32, n, frames, wts, ng, feat.as<float>(), ldf,
-                                           filt.as<float>(), s));
+                                           filt.as<float>(), 8, s));      // dual filter rows
                         filt_ptr = filt.as<float>();
-                        ldfilt = 4;
+                        ldfilt = 8;
                         R(mmmp_fk_chain_f64(w, robot, nq64.as<double>(), D, n, pos64.as<double>(), s));
                     }
                     feat_ptr = feat.as<float>();
@@ -218,7 +239,7 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                 int* any_amb = reinterpret_cast<int*>(amb.as<uint8_t>() + ((n + 3) & ~(int64_t)3));
                 for (int attempt = 0; attempt < 2 && rc == MMMP_OK; ++attempt) {
                     R(mmmp_knn(filt_ptr, feat_ptr, n, filt_ptr, feat_ptr, n, ldfilt,
-                               ldfilt == 4 && filt_ptr != feat_ptr ? 3 : m32.dim, ldf, &m32, kc, 1, 0, 0,
+                               filt_ptr != feat_ptr ? 6 : m32.dim, ldf, &m32, kc, 1, 0, 0,
                                cidx.as<int32_t>(), cdist.as<float>(), s));
                     if (attempt == 0) cudaEventRecord(ev[4], s);
                     R(mmmp_knn_refine(ref64_ptr, ref64_ptr, ld64, &m64, cidx.as<int32_t>(), cdist.as<float>(), n, kc, k,
@@ -228,36 +249,99 @@ extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, cons
                     T(cudaMemsetAsync(any_amb, 0, sizeof(int), s));
                     int g = mmmp_div_up(n, 256);
                     MMMP_LAUNCH(any_flag_kernel, g > 148 * 8 ? 148 * 8 : g, 256, 0, s, amb.as<uint8_t>(), n, any_amb);
+                    T(cudaPeekAtLastError());
                     T(cudaMemcpyAsync(&flagged, any_amb, sizeof(int), cudaMemcpyDeviceToHost, s));
                     T(cudaStreamSynchronize(s));
                     if (!flagged) break;
                     kc = kc_wide;
                 }
                 cudaEventRecord(ev[5], s);
+                // the neighbour tables go home on the copy stream while the edges are checked
+                cudaEventRecord(ready, s);
+                cudaStreamWaitEvent(s2, ready, 0);
+                T(cudaMemcpyAsync(node_src_h, idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s2));
+                T(cudaMemcpyAsync(nbr_idx_h, ridx.p, sizeof(int32_t) * n * k, cudaMemcpyDeviceToHost, s2));
+                if (nbr_dist_h) T(cudaMemcpyAsync(nbr_dist_h, rdist.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, s2));
                 R(mmmp_edges_from_knn(ridx.as<int32_t>(), n, k, edges.as<int32_t>(), s));
                 R(mmmp_collide_edges(w, robot, nq32.p, ld32, edges.as<int32_t>(), n * k, n_steps, step, flags,
                                      ecoll.as<uint8_t>(), s));
                 int g = mmmp_div_up(n * k, 256);
                 if (g > 148 * 16) g = 148 * 16;
                 MMMP_LAUNCH(invert_flags_kernel, g, 256, 0, s, ecoll.as<uint8_t>(), n * k);
+                T(cudaPeekAtLastError());
                 cudaEventRecord(ev[6], s);
-                T(cudaMemcpyAsync(node_src_h, idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
-                T(cudaMemcpyAsync(nbr_idx_h, ridx.p, sizeof(int32_t) * n * k, cudaMemcpyDeviceToHost, s));
-                if (nbr_dist_h) T(cudaMemcpyAsync(nbr_dist_h, rdist.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, s));
-                T(cudaMemcpyAsync(edge_free_h, ecoll.p, (size_t)n * k, cudaMemcpyDeviceToHost, s));
-                cudaEventRecord(ev[7], s);
+                // ... and the verdicts while the accept pass runs
+                cudaEventRecord(ready, s);
+                cudaStreamWaitEvent(s2, ready, 0);
+                T(cudaMemcpyAsync(edge_free_h, ecoll.p, (size_t)n * k, cudaMemcpyDeviceToHost, s2));
+                if (k2 > 0 && rc == MMMP_OK) {
+                    T(adj.alloc(sizeof(int32_t) * n * k2));
+                    T(deg.alloc(sizeof(int32_t) * n));
+                    T(labels.alloc(sizeof(int32_t) * n));
+                    T(ncomp.alloc(sizeof(int64_t)));
+                    if (rc == MMMP_OK) {
+                        R(mmmp_greedy_degree_connect_device(ridx.as<int32_t>(), ecoll.as<uint8_t>(), n, k, k2, k2,
+                                                            adj.as<int32_t>(), deg.as<int32_t>(), nullptr, s));
+                        cudaEventRecord(ev[7], s);
+                        R(mmmp_connected_components(adj.as<int32_t>(), nullptr, n, k2, labels.as<int32_t>(),
+                                                    ncomp.as<int64_t>(), s));
+                        cudaEventRecord(ev[8], s);
+                        T(cudaMemcpyAsync(adj_h, adj.p, sizeof(int32_t) * n * k2, cudaMemcpyDeviceToHost, s));
+                        T(cudaMemcpyAsync(deg_h, deg.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+                        if (labels_h) T(cudaMemcpyAsync(labels_h, labels.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+                        if (n_components_h)
+                            T(cudaMemcpyAsync(n_components_h, ncomp.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+                    }
+                } else {
+                    cudaEventRecord(ev[7], s);
+                    cudaEventRecord(ev[8], s);
+                }
+                cudaEventRecord(ready, s2);
+                cudaStreamWaitEvent(s, ready, 0);        // "d2h" ends when both streams have delivered
+                cudaEventRecord(ev[9], s);
                 T(cudaStreamSynchronize(s));
+                T(cudaStreamSynchronize(s2));
                 if (rc == MMMP_OK && timings_ms_h) {
-                    for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&timings_ms_h[i], ev[i], ev[i + 1]);
-                    cudaEventElapsedTime(&timings_ms_h[7], ev[0], ev[7]);
+                    // h2d, accept test + compaction, features, scan, re-rank, edge collision, [6] d2h tail,
+                    // [7] total, [8] accept pass, [9] components
+                    for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&timings_ms_h[i], ev[i], ev[i + 1]);
+                    cudaEventElapsedTime(&timings_ms_h[6], ev[8], ev[9]);
+                    cudaEventElapsedTime(&timings_ms_h[7], ev[0], ev[9]);
+                    cudaEventElapsedTime(&timings_ms_h[8], ev[6], ev[7]);
+                    cudaEventElapsedTime(&timings_ms_h[9], ev[7], ev[8]);
                 }
             }
         }
     }
     *n_nodes_h = n_nodes;
     for (auto& e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(ready);
+    cudaStreamDestroy(s2);
     cudaStreamDestroy(s);
     return rc;
+}
+
+extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D,
+                                            int metric_kind, int k, int n_steps, double step, uint32_t flags,
+                                            int64_t* n_nodes_h, int32_t* node_src_h, int32_t* nbr_idx_h,
+                                            double* nbr_dist_h, uint8_t* edge_free_h, float* timings_ms_h) {
+    float t[10] = {0};
+    const int rc = roadmap_host_impl(w, robot, q64_h, N, D, metric_kind, k, n_steps, step, flags, 0, n_nodes_h, node_src_h,
+                                     nbr_idx_h, nbr_dist_h, edge_free_h, nullptr, nullptr, nullptr, nullptr,
+                                     timings_ms_h ? t : nullptr);
+    if (timings_ms_h)
+        for (int i = 0; i < 8; ++i) timings_ms_h[i] = t[i];
+    return rc;
+}
+
+extern "C" int mmmp_roadmap_build_host(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D,
+                                       int metric_kind, int k1, int k2, int n_steps, double step, uint32_t flags,
+                                       int64_t* n_nodes_h, int32_t* node_src_h, int32_t* nbr_idx_h, double* nbr_dist_h,
+                                       uint8_t* edge_free_h, int32_t* adj_h, int32_t* deg_h, int32_t* labels_h,
+                                       int64_t* n_components_h, float* timings_ms_h) {
+    if (k2 < 1) return MMMP_ERR_ARG;
+    return roadmap_host_impl(w, robot, q64_h, N, D, metric_kind, k1, n_steps, step, flags, k2, n_nodes_h, node_src_h,
+                             nbr_idx_h, nbr_dist_h, edge_free_h, adj_h, deg_h, labels_h, n_components_h, timings_ms_h);
 }
 
 // Greedy accept pass, reference decoupled_prm.py:480-504: nodes in id order,
@@ -272,7 +356,7 @@ extern "C" int mmmp_greedy_degree_connect(const int32_t* nbr_idx, const uint8_t*
         for (int c = 0; c < k1; ++c) {
             if (deg[i] == k2) break;
             const int32_t j = nbr_idx[i * k1 + c];
-            if (j < 0 || j >= N) continue;
+            if (j < 0 || j >= N || j == i) continue;
             if (!edge_free[i * k1 + c]) continue;
             bool present = false;
             for (int t = 0; t < deg[i]; ++t)

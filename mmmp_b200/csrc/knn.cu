@@ -301,3 +301,77 @@ extern "C" int mmmp_radius(const float* ref, const double* ref64, int64_t n_ref,
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }
+
+// ---- packed neighbour records: the post-search exchange of a sharded search ------------------
+// A rank that answered m query rows of a sharded search (mmmp_knn_range + mmmp_knn_refine) packs
+// them as records of 2 + 3k 32-bit words -- [row id, ambiguous, idx[k], dist[k] (fp64 as two
+// words)] -- so that ONE all-gather ships everything, and every rank scatters the gathered
+// records into tables in the caller's row order with one kernel.  Records beyond m (padding up
+// to the fixed block size of the collective) carry row id -1 and are skipped by the scatter.
+namespace {
+
+__global__ void __launch_bounds__(256)
+pack_records_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ idx, const double* __restrict__ dist,
+                    const uint8_t* __restrict__ amb, int64_t m, int k, int64_t cap, uint32_t* __restrict__ rec) {
+    const int rw = 2 + 3 * k;
+    const int64_t total = cap * rw;
+    const uint32_t* dist_w = reinterpret_cast<const uint32_t*>(dist);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / rw;
+        const int c = (int)(t - r * rw);
+        uint32_t v = 0;
+        if (r >= m) v = c == 0 ? 0xffffffffu : 0u;
+        else if (c == 0) v = (uint32_t)rows[r];
+        else if (c == 1) v = amb ? amb[r] : 0u;
+        else if (c < 2 + k) v = (uint32_t)idx[r * k + (c - 2)];
+        else v = dist_w[r * 2 * k + (c - 2 - k)];
+        rec[t] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_records_kernel(const uint32_t* __restrict__ rec, int64_t total_rec, int k, int64_t n, int32_t* __restrict__ idx,
+                       double* __restrict__ dist, uint8_t* __restrict__ amb) {
+    const int rw = 2 + 3 * k;
+    const int64_t total = total_rec * rw;
+    uint32_t* dist_w = reinterpret_cast<uint32_t*>(dist);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / rw;
+        const int c = (int)(t - r * rw);
+        const int64_t row = (int32_t)rec[r * rw];
+        if (row < 0 || row >= n || c == 0) continue;
+        const uint32_t v = rec[t];
+        if (c == 1) {
+            if (amb) amb[row] = (uint8_t)v;
+        } else if (c < 2 + k) {
+            idx[row * k + (c - 2)] = (int32_t)v;
+        } else if (dist) {
+            dist_w[row * 2 * k + (c - 2 - k)] = v;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int mmmp_pack_neighbour_records(const int32_t* rows_d, const int32_t* idx_d, const double* dist_d,
+                                           const uint8_t* amb_d, int64_t m, int k, int64_t cap, void* rec_d,
+                                           void* stream) {
+    if (!rows_d || !idx_d || !dist_d || !rec_d || m < 0 || cap < m || k < 1 || k > MMMP_MAX_K) return MMMP_ERR_ARG;
+    if (cap == 0) return MMMP_OK;
+    int g = mmmp_div_up(cap * (2 + 3 * k), 256);
+    if (g > 148 * 16) g = 148 * 16;
+    MMMP_LAUNCH(pack_records_kernel, g, 256, 0, stream, rows_d, idx_d, dist_d, amb_d, m, k, cap, (uint32_t*)rec_d);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_scatter_neighbour_records(const void* rec_d, int64_t n_records, int k, int64_t n, int32_t* idx_d,
+                                              double* dist_d, uint8_t* amb_d, void* stream) {
+    if (!rec_d || !idx_d || n_records < 0 || n < 0 || k < 1 || k > MMMP_MAX_K) return MMMP_ERR_ARG;
+    if (n_records == 0) return MMMP_OK;
+    int g = mmmp_div_up(n_records * (2 + 3 * k), 256);
+    if (g > 148 * 16) g = 148 * 16;
+    MMMP_LAUNCH(scatter_records_kernel, g, 256, 0, stream, (const uint32_t*)rec_d, n_records, k, n, idx_d, dist_d, amb_d);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}

@@ -66,18 +66,30 @@ constexpr int KNN_TILE = MMMP_KNN_TILE;        // reference rows per shared-memo
 #ifndef MMMP_KNN_RU
 #define MMMP_KNN_RU 8
 #endif
-constexpr int KNN_RU = MMMP_KNN_RU;            // rows per inner-loop step
+// rows per inner-loop step: the step holds 2 x RU x F4 float4 of reference rows in registers (this
+// step and the prefetched next one), so wider rows take fewer per step -- 8 rows of 4 columns, 4 of
+// 8, 2 of 16, 1 of 32: 64 registers each.  (With 8 rows for every width the 16-column kernel needed
+// 185 registers and the 32-column one spilled 636 B: profiles/r01_ptxas_resources.csv.)
+__host__ __device__ constexpr int knn_ru(int F4) {
+    return F4 == 1 ? MMMP_KNN_RU : (F4 == 2 ? 4 : (F4 == 4 ? 2 : 1));
+}
 #ifndef MMMP_KNN_QSLACK
 #define MMMP_KNN_QSLACK 12
 #endif
 constexpr int KNN_QSLACK = MMMP_KNN_QSLACK;    // queue entries a thread may hold before its warp drains
-constexpr int KNN_QC = KNN_RU + KNN_QSLACK;    // queue capacity per (thread, query)
+__host__ __device__ constexpr int knn_qc(int F4) { return knn_ru(F4) + KNN_QSLACK; }  // queue capacity per (thread, query)
 #ifndef MMMP_KNN_MINB
 #define MMMP_KNN_MINB 5                        // resident CTAs per SM the register budget must allow, 4-column filter
                                                // rows (71 registers); 8 columns: 3 CTAs, 113 registers (5 would spill 348 B)
 #endif
 #ifndef MMMP_KNN_MINB2
-#define MMMP_KNN_MINB2 3                       // the same for 8-column filter rows (joint-space L2 of a 7-DOF arm)
+#define MMMP_KNN_MINB2 4                       // the same for 8-column filter rows (joint-space L2 of a 7-DOF arm, dual FK rows)
+#endif
+#ifndef MMMP_KNN_MINB4
+#define MMMP_KNN_MINB4 3                       // 16-column rows (14-D composite configurations)
+#endif
+#ifndef MMMP_KNN_MINB8
+#define MMMP_KNN_MINB8 2                       // 32-column rows (28-D composite configurations)
 #endif
 #ifndef MMMP_KNN_WALK
 #define MMMP_KNN_WALK 2                         // producer: blocks of 16 tile boxes per side and walk step (1/2/4/8: 27.5/27.3/27.3/28.4 ms)
@@ -253,12 +265,25 @@ cell_order_kernel(const int32_t* __restrict__ in, const int64_t* __restrict__ of
 
 // ---- row packing ----------------------------------------------------------------------
 // filter rows: out[p] = [in[perm[p]][0..d), 0 .., (1 - eps) * |.|^2]   (W columns); perm may be NULL
+// dual rows (W = 8, d = 6): out[p] = [c0 c1 c2 d0 d1 d2, (1 - eps) |c|^2, (1 - eps) |d|^2]
 __global__ void __launch_bounds__(256)
 knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, const int32_t* __restrict__ perm,
-                float* __restrict__ out, int W) {
+                float* __restrict__ out, int W, int dual) {
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const float* r = in + (int64_t)(perm ? perm[p] : p) * ld_in;
         float* o = out + p * W;
+        if (dual) {
+            float nc = 0.f, nd = 0.f;
+            for (int c = 0; c < 6; ++c) {
+                const float v = r[c];
+                o[c] = v;
+                if (c < 3) nc = fmaf(v, v, nc);
+                else nd = fmaf(v, v, nd);
+            }
+            o[6] = nc * (1.f - KNN_SLACK);
+            o[7] = nd * (1.f - KNN_SLACK);
+            continue;
+        }
         float acc = 0.f;
         for (int c = 0; c < W - 1; ++c) {
             const float v = c < d ? r[c] : 0.f;
@@ -377,15 +402,22 @@ struct ScanCtl {                  // per-CTA control block in shared memory
 
 // shared-memory layout (floats unless noted), LS = KNN_CTHREADS * Q:
 //   ring[STAGES][ TILE*W filter | TILE*S exact ]  lv[kc][LS]  li[kc][LS]  xq[S][LS]
-//   warp queues (u16) [CWARPS][32*Q*QC]   bars[2*STAGES] (u64)   ctl
+//   warp queues (u16) [CWARPS][32*Q*QC(F4)]   bars[2*STAGES] (u64)   ctl
 __host__ __device__ constexpr size_t knn_stage_floats(int W, int S) { return (size_t)KNN_TILE * (W + S); }
 __host__ __device__ constexpr size_t knn_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-template <int F4, int Q>
-__global__ void __launch_bounds__(KNN_THREADS, F4 == 1 ? MMMP_KNN_MINB : (F4 == 2 ? MMMP_KNN_MINB2 : 1))
+// DUAL (F4 = 2 only): the filter rows are the dual rows of mmmp_fk_features, two tests per pair --
+//   |dC|^2 <= tau^2   and   |dC|^2 + |dD|^2 <= 2 tau^2
+// -- thr1 / thr hold the two thresholds, tauf stays the C-domain bound the tile culling uses.
+template <int F4, int Q, bool DUAL>
+__global__ void __launch_bounds__(KNN_THREADS, F4 == 1 ? MMMP_KNN_MINB : (F4 == 2 ? MMMP_KNN_MINB2 :
+                                               (F4 == 4 ? MMMP_KNN_MINB4 : MMMP_KNN_MINB8)))
 knn_scan_kernel(const __grid_constant__ KnnArgs A) {
+    static_assert(!DUAL || F4 == 2, "dual rows are 8 columns wide");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int W = F4 * 4;
+    constexpr int KNN_RU = knn_ru(F4);
+    constexpr int KNN_QC = knn_qc(F4);
     constexpr int LS = KNN_CTHREADS * Q;  // column stride of the per-query shared arrays
     const int S = A.S;
     const int kc = A.kc;
@@ -427,7 +459,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
 
     // ---- queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q),
     //      exact row in this thread's shared-memory column ----
-    float a2[Q][W - 1], thr[Q], Aq[Q], tauf[Q];
+    float a2[Q][W - 1], thr[Q], thr1[Q], Aq[Q], Aq1[Q], tauf[Q];
     int64_t qrow[Q];
     if (tid < KNN_CTHREADS) {
         float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -446,7 +478,14 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                 }
             }
             Aq[qq] = valid ? __ldg(A.pquery + qi * W + (W - 1)) : 0.f;
+            Aq1[qq] = 0.f;
+            if (DUAL) {  // columns 6, 7 of a packed dual row are the two norms, not coordinates
+                Aq1[qq] = -0.5f * a2[qq][6];
+                Aq[qq] += Aq1[qq];
+                a2[qq][6] = 0.f;
+            }
             thr[qq] = valid ? CUDART_INF_F : -CUDART_INF_F;
+            thr1[qq] = thr[qq];
             tauf[qq] = valid ? CUDART_INF_F : 0.f;
             qrow[qq] = valid ? (A.qperm ? (int64_t)__ldg(A.qperm + qi) : qi) : 0;
             for (int c = 0; c < S; ++c)
@@ -674,7 +713,8 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             const float tau = lv[(size_t)(kc - 1) * LS + qq * KNN_CTHREADS + tid];
             if (tau < CUDART_INF_F) {
                 const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
-                thr[qq] = tf - Aq[qq];
+                thr[qq] = (DUAL ? 2.f * tf : tf) - Aq[qq];
+                thr1[qq] = tf - Aq1[qq];
                 tauf[qq] = tf;
             }
             worst = fmaxf(worst, tauf[qq]);
@@ -723,26 +763,35 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                 for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
                     for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)((jn + u) * W + 4 * i) * 4);
-                float sv[Q][KNN_RU];
-                float worst = CUDART_INF_F;  // min over queries of (best filter value - threshold)
+                float sv[Q][KNN_RU];         // filter value - threshold (DUAL: the larger of the two)
+                float worst = CUDART_INF_F;  // min over queries and rows
 #pragma unroll
                 for (int qq = 0; qq < Q; ++qq) {
 #pragma unroll
                     for (int u = 0; u < KNN_RU; ++u) {
-                        float acc = r[u][F4 - 1].w;  // B_r
+                        if (DUAL) {
+                            // row = (c0 c1 c2 d0 | d1 d2 nC nD)
+                            const float accC = fmaf(a2[qq][0], r[u][0].x, fmaf(a2[qq][1], r[u][0].y,
+                                                    fmaf(a2[qq][2], r[u][0].z, r[u][F4 - 1].z)));
+                            const float accD = fmaf(a2[qq][3], r[u][0].w, fmaf(a2[qq][4], r[u][F4 - 1].x,
+                                                    fmaf(a2[qq][5], r[u][F4 - 1].y, r[u][F4 - 1].w)));
+                            sv[qq][u] = fmaxf(accC - thr1[qq], accC + accD - thr[qq]);
+                        } else {
+                            float acc = r[u][F4 - 1].w;  // B_r
 #pragma unroll
-                        for (int i = 0; i < F4; ++i) {
-                            acc = fmaf(a2[qq][4 * i + 0], r[u][i].x, acc);
-                            acc = fmaf(a2[qq][4 * i + 1], r[u][i].y, acc);
-                            acc = fmaf(a2[qq][4 * i + 2], r[u][i].z, acc);
-                            if (i < F4 - 1) acc = fmaf(a2[qq][4 * i + 3], r[u][i].w, acc);
+                            for (int i = 0; i < F4; ++i) {
+                                acc = fmaf(a2[qq][4 * i + 0], r[u][i].x, acc);
+                                acc = fmaf(a2[qq][4 * i + 1], r[u][i].y, acc);
+                                acc = fmaf(a2[qq][4 * i + 2], r[u][i].z, acc);
+                                if (i < F4 - 1) acc = fmaf(a2[qq][4 * i + 3], r[u][i].w, acc);
+                            }
+                            sv[qq][u] = acc - thr[qq];
                         }
-                        sv[qq][u] = acc;
                     }
                     float m = sv[qq][0];
 #pragma unroll
                     for (int u = 1; u < KNN_RU; ++u) m = fminf(m, sv[qq][u]);
-                    worst = fminf(worst, m - thr[qq]);
+                    worst = fminf(worst, m);
                 }
                 // one warp-uniform branch per step
                 if (__any_sync(0xffffffffu, worst <= 0.f)) {
@@ -750,7 +799,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                     for (int qq = 0; qq < Q; ++qq) {
 #pragma unroll
                         for (int u = 0; u < KNN_RU; ++u) {
-                            const bool hit = sv[qq][u] <= thr[qq];
+                            const bool hit = sv[qq][u] <= 0.f;
                             const unsigned m = __ballot_sync(0xffffffffu, hit);
                             if (hit)
                                 wq[wcnt + __popc(m & lanes_below)] =
@@ -845,16 +894,16 @@ int fill_metric(const mmmp_metric* m, int ldx, MetricDev& M) {
 size_t scan_smem(int F4, int Q, int kc, int S) {
     const size_t w = F4 * 4, ls = (size_t)KNN_CTHREADS * Q;
     size_t b = (size_t)KNN_STAGES * knn_stage_floats((int)w, S) * 4 + (size_t)kc * ls * 8 + (size_t)S * ls * 4;
-    b = knn_align(b + (size_t)Q * KNN_QC * KNN_CTHREADS * 2, 8);
+    b = knn_align(b + (size_t)Q * knn_qc(F4) * KNN_CTHREADS * 2, 8);
     return b + 2 * KNN_STAGES * 8 + sizeof(ScanCtl) + 16;
 }
 
-template <int F4, int Q>
+template <int F4, int Q, bool DUAL = false>
 int launch_scan(const KnnArgs& A, int n_qblocks, void* stream) {
     const size_t smem = scan_smem(F4, Q, A.kc, A.S);
-    MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_qblocks, A.n_splits, 1);
-    MMMP_LAUNCH((knn_scan_kernel<F4, Q>), grid, KNN_THREADS, smem, stream, A);
+    MMMP_LAUNCH((knn_scan_kernel<F4, Q, DUAL>), grid, KNN_THREADS, smem, stream, A);
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }
@@ -938,6 +987,8 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     if (rc) return rc;
     const int W = width_for(fdim);
     if (!W) return MMMP_ERR_LIMIT;
+    // dual rows of mmmp_fk_features: (C, D, 0, 0), two tests per pair (see the kernel)
+    const int dual = (A.M.kind == MMMP_METRIC_GROUP_L2_SUM && fdim == 6 && ldf >= 8) ? 1 : 0;
     const int F4 = W / 4;
     const int S = A.M.dim | 1;  // odd row stride: exact rows of a tile fall into distinct banks
     if (n_query == 0) return MMMP_OK;
@@ -950,7 +1001,7 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     // queries per thread: measured on B200 (1M x 1M, FK and joint-space metrics), one query per
     // thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM
     const bool ranged = frac_lo >= 0.0;
-    const int qmax = (F4 <= 2 && !ranged) ? 2 : 1;
+    const int qmax = (F4 <= 2 && !ranged && !dual) ? 2 : 1;
     int Q = 1;
     if (const char* e = getenv("MMMP_KNN_Q")) {
         const int q = atoi(e);
@@ -1032,7 +1083,7 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
         KNN_TRY(cudaMallocAsync(&boxes, sizeof(float) * 6 * (total_tiles > 0 ? total_tiles : 1), s));
     }
     if (n_ref > 0) {
-        MMMP_LAUNCH(knn_pack_kernel, grid_for(n_ref, sms), 256, 0, stream, fref, ldf, fdim, n_ref, perm, pref, W);
+        MMMP_LAUNCH(knn_pack_kernel, grid_for(n_ref, sms), 256, 0, stream, fref, ldf, fdim, n_ref, perm, pref, W, dual);
         MMMP_LAUNCH(knn_pack_exact_kernel, grid_for(n_ref4 * S, sms), 256, 0, stream, xref, ldx, A.M.dim, n_ref, n_ref4,
                     perm, xs, S);
     }
@@ -1040,7 +1091,8 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
         pquery = pref;
         qperm = perm;
     } else {
-        MMMP_LAUNCH(knn_pack_kernel, grid_for(n_query, sms), 256, 0, stream, fquery, ldf, fdim, n_query, qperm, pquery, W);
+        MMMP_LAUNCH(knn_pack_kernel, grid_for(n_query, sms), 256, 0, stream, fquery, ldf, fdim, n_query, qperm, pquery, W,
+                    dual);
     }
     if (cull && total_tiles > 0)
         MMMP_LAUNCH(tile_box_kernel, (int)total_tiles, KNN_TILE, 0, stream, pref, W, nd, n_ref, boxes);
@@ -1066,7 +1118,8 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     A.stats = g_knn_stats;
     A.out_idx = tmp_idx;
     A.out_val = tmp_val;
-    switch (F4 * 10 + Q) {
+    switch (dual ? 0 : F4 * 10 + Q) {
+        case 0: rc = launch_scan<2, 1, true>(A, n_qblocks, stream); break;
         case 11: rc = launch_scan<1, 1>(A, n_qblocks, stream); break;
         case 12: rc = launch_scan<1, 2>(A, n_qblocks, stream); break;
         case 21: rc = launch_scan<2, 1>(A, n_qblocks, stream); break;

@@ -72,6 +72,77 @@ static void bounding_sphere(const float4* sp, int n, float4* out) {
     *out = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(r * (1.0 + 1e-6) + 1e-7));
 }
 
+// Bounding capsule of a set of spheres: axis = principal direction of the centres through their
+// mean, radius = largest (distance from the axis line + sphere radius), segment ends pulled in as
+// far as the hemispherical caps allow; the radius is then recomputed from the final segment so
+// that containment holds by construction.
+static void bounding_capsule(const float4* sp, int n, float4* out_a, float4* out_b) {
+    if (n <= 0) {
+        *out_a = make_float4(0.f, 0.f, 0.f, -1.f);
+        *out_b = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    double mean[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        mean[0] += sp[i].x;
+        mean[1] += sp[i].y;
+        mean[2] += sp[i].z;
+    }
+    for (int k = 0; k < 3; ++k) mean[k] /= n;
+    double C[3][3] = {{0}};
+    for (int i = 0; i < n; ++i) {
+        const double d[3] = {sp[i].x - mean[0], sp[i].y - mean[1], sp[i].z - mean[2]};
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) C[a][b] += d[a] * d[b];
+    }
+    double u[3] = {1.0, 0.7, 0.4};
+    for (int it = 0; it < 200; ++it) {  // power iteration
+        double v[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) v[a] += C[a][b] * u[b];
+        const double nv = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (nv < 1e-30) break;  // all centres coincide: any axis
+        for (int a = 0; a < 3; ++a) u[a] = v[a] / nv;
+    }
+    {
+        const double nu = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        for (int a = 0; a < 3; ++a) u[a] /= nu;
+    }
+    double R = 0;
+    for (int i = 0; i < n; ++i) {
+        const double d[3] = {sp[i].x - mean[0], sp[i].y - mean[1], sp[i].z - mean[2]};
+        const double t = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+        const double perp = std::sqrt(std::max(0.0, d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - t * t));
+        R = std::max(R, perp + sp[i].w);
+    }
+    double t_lo = 1e300, t_hi = -1e300;  // the segment may end where the caps still cover everything
+    for (int i = 0; i < n; ++i) {
+        const double d[3] = {sp[i].x - mean[0], sp[i].y - mean[1], sp[i].z - mean[2]};
+        const double t = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+        const double perp2 = std::max(0.0, d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - t * t);
+        const double reach = std::sqrt(std::max(0.0, (R - sp[i].w) * (R - sp[i].w) - perp2));
+        t_lo = std::min(t_lo, t + reach);
+        t_hi = std::max(t_hi, t - reach);
+    }
+    if (t_lo > t_hi) t_lo = t_hi = 0.5 * (t_lo + t_hi);
+    const double a[3] = {mean[0] + t_lo * u[0], mean[1] + t_lo * u[1], mean[2] + t_lo * u[2]};
+    const double b[3] = {mean[0] + t_hi * u[0], mean[1] + t_hi * u[1], mean[2] + t_hi * u[2]};
+    const float af[3] = {(float)a[0], (float)a[1], (float)a[2]}, bf[3] = {(float)b[0], (float)b[1], (float)b[2]};
+    // radius from the segment as the kernels will see it (fp32 end points)
+    double rad = 0;
+    const double ab[3] = {(double)bf[0] - af[0], (double)bf[1] - af[1], (double)bf[2] - af[2]};
+    const double ab2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+    for (int i = 0; i < n; ++i) {
+        const double d[3] = {sp[i].x - (double)af[0], sp[i].y - (double)af[1], sp[i].z - (double)af[2]};
+        double t = ab2 > 0 ? (d[0] * ab[0] + d[1] * ab[1] + d[2] * ab[2]) / ab2 : 0.0;
+        t = std::min(1.0, std::max(0.0, t));
+        const double e[3] = {d[0] - t * ab[0], d[1] - t * ab[1], d[2] - t * ab[2]};
+        rad = std::max(rad, std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + sp[i].w);
+    }
+    *out_a = make_float4(af[0], af[1], af[2], (float)(rad * (1.0 + 1e-6) + 1e-6));
+    *out_b = make_float4(bf[0], bf[1], bf[2], 0.f);
+}
+
 extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
                                  const mmmp_obstacle_desc* obstacles, int n_obstacles,
                                  mmmp_world** out) {
@@ -151,6 +222,8 @@ extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
         for (int l = 0; l < d.n_links; ++l) {
             bounding_sphere(R.sphere + R.link_sphere_begin[l], R.link_sphere_begin[l + 1] - R.link_sphere_begin[l],
                             &R.link_bound[l]);
+            bounding_capsule(R.sphere + R.link_sphere_begin[l], R.link_sphere_begin[l + 1] - R.link_sphere_begin[l],
+                             &R.cap_a[l], &R.cap_b[l]);
             if (R.link_frame[l] != 0) R.n_moving_links++;
         }
         // reach[m][f]: lever arm of joint m over the sphere centres of frame f (f > m), an upper

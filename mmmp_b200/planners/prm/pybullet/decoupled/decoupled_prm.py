@@ -261,17 +261,37 @@ class DecoupledPRM:
     def sample_safe_poses(self, r_id, sigma=0.2):
         return safe_poses()
 
-    def _sample_around(self, r_id, q0, n, sigma=0.2):
+    def sample_around_task_space_position(self, pos, sigma):
+        """:465-470: three draws from numpy's global stream, x then y then z."""
+        x, y, z = pos
+        x += np.random.normal(0, sigma)
+        y += np.random.normal(0, sigma)
+        z += np.random.normal(0, sigma)
+        return [x, y, z]
+
+    def _sample_around_pose(self, r_id, pose, n):
+        """sample_start_poses / sample_goal_poses (:438-462): n tool positions drawn around the
+        tool position of `pose` (sigma 0.2 m, same draws in the same order as the reference),
+        each solved by closest IK from `pose` with the tool pointing down (quaternion of Euler
+        (180 deg, 0, 0)) -- one batched mmmp_ik_dls launch instead of n pybullet calls.  The tool
+        positions are the reference's; the joint values come from this library's DLS solver
+        (pybullet's IK arithmetic is not available: parity unpinned)."""
         r_index = self.r_ids.index(r_id)
-        lo = np.array([iv.lower for iv in self.c_spaces[r_index]])
-        hi = np.array([iv.upper for iv in self.c_spaces[r_index]])
-        return [np.clip(np.asarray(q0, float) + self._rng.normal(0, sigma, len(lo)), lo, hi) for _ in range(n)]
+        model = self.robot_models[r_index]
+        pose = np.asarray(pose, dtype=float)[:7]
+        pos0 = model.position_from_fk(pose)
+        targets = np.array([self.sample_around_task_space_position(pos0, 0.2) for _ in range(n)], dtype=np.float64)
+        dev = core._require_cuda()
+        tq = torch.tensor(np.tile((1.0, 0.0, 0.0, 0.0), (n, 1)), dtype=torch.float64, device=dev)
+        q0 = torch.tensor(pose[None], dtype=torch.float64, device=dev)
+        q, _, _ = self.env.world.ik(torch.tensor(targets, dtype=torch.float64, device=dev), tq, q0, r_index)
+        return [row for row in q.cpu().numpy()]
 
     def sample_start_poses(self, r_id, n=10):
-        return self._sample_around(r_id, self.agents[self.r_ids.index(r_id)]['start'], n)
+        return self._sample_around_pose(r_id, self.agents[self.r_ids.index(r_id)]['start'], n)
 
     def sample_goal_poses(self, r_id, n=10):
-        return self._sample_around(r_id, self.agents[self.r_ids.index(r_id)]['goal'], n)
+        return self._sample_around_pose(r_id, self.agents[self.r_ids.index(r_id)]['goal'], n)
 
     # ------------------------------------------------------------------ connection
     def _edges_hit(self, r_index, q32, edges):

@@ -76,14 +76,15 @@ def all_gather_padded(t: torch.Tensor, cap: int, size: int, group=None, fill=0) 
     import torch.distributed as dist
     pad = torch.full((cap,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
-    out = torch.empty((size * cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    try:
+    if t.is_cuda:       # NCCL: one flat collective
+        out = torch.empty((size * cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, pad, group=group)
-    except (RuntimeError, NotImplementedError):      # backends without the flat form
-        parts = [torch.empty_like(pad) for _ in range(size)]
-        dist.all_gather(parts, pad, group=group)
-        out = torch.cat(parts, 0)
-    return out
+        return out
+    # CPU tensors (gloo, the host-logic tests): the list form; chosen by where the data lives, never
+    # by catching a failed collective -- a rank that fails must fail, not issue a second collective
+    parts = [torch.empty_like(pad) for _ in range(size)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat(parts, 0)
 
 
 def balanced_cuts(cuts, times, damping: float = 0.5):
@@ -102,6 +103,76 @@ def balanced_cuts(cuts, times, damping: float = 0.5):
     out = np.concatenate([[0.0], np.cumsum(width)])
     out[-1] = 1.0
     return out
+
+
+def arm_layout(world_size: int, n_arms: int):
+    """Which ranks build which arm's roadmap (in decoupled planners every arm's roadmap
+    is independent).  -> ranks_of_arm: list of rank lists, one per arm.
+      world_size <= n_arms : arm a belongs to rank a % world_size alone -- no data-path collective;
+      world_size a multiple of n_arms : world_size / n_arms consecutive ranks share an arm
+                             (sharded sampling, neighbour search and edge checks inside the team);
+      otherwise            : every arm is sharded over all ranks."""
+    if world_size <= n_arms:
+        return [[a % world_size] for a in range(n_arms)]
+    if world_size % n_arms == 0:
+        per = world_size // n_arms
+        return [list(range(a * per, (a + 1) * per)) for a in range(n_arms)]
+    return [list(range(world_size)) for _ in range(n_arms)]
+
+
+class ArmTeams:
+    """The process groups of an arm-parallel build and the final hand-over of every arm's result to
+    rank 0 ("adjacency resident on rank 0").  Every rank must construct it (new_group is
+    collective)."""
+
+    def __init__(self, n_arms: int, rank: Optional[int] = None, world_size: Optional[int] = None):
+        import torch.distributed as dist
+        live = dist.is_available() and dist.is_initialized()
+        self.rank = (dist.get_rank() if live else 0) if rank is None else rank
+        self.world_size = (dist.get_world_size() if live else 1) if world_size is None else world_size
+        self.ranks_of_arm = arm_layout(self.world_size, n_arms)
+        self.groups = {}
+        made = {}
+        for a, ranks in enumerate(self.ranks_of_arm):
+            key = tuple(ranks)
+            if len(ranks) > 1 and len(ranks) < self.world_size and key not in made:
+                made[key] = dist.new_group(list(ranks))           # every rank calls, in the same order
+            self.groups[a] = made.get(key)                         # None: alone, or the whole world
+        self.my_arms = [a for a, ranks in enumerate(self.ranks_of_arm) if self.rank in ranks]
+
+    def team(self, arm: int):
+        """(group, single_rank) arguments of the RoadmapBuilder of `arm` on this rank."""
+        ranks = self.ranks_of_arm[arm]
+        return self.groups[arm], len(ranks) == 1
+
+    def leader(self, arm: int) -> int:
+        return self.ranks_of_arm[arm][0]
+
+    def collect_on_root(self, per_arm: dict, like: dict):
+        """per_arm[a] = list of tensors this rank holds for its arm a (identical on every rank of
+        the team); like[a] = list of (shape, dtype) of every arm's tensors.  Rank 0 ends up with
+        the tensors of ALL arms (returns {arm: [tensors]}); leaders of the other arms send theirs
+        point to point, everything in one batch so that no ordering between pairs can dead-lock."""
+        import torch.distributed as dist
+        if self.world_size == 1:
+            return per_arm
+        ops, got = [], {}
+        for a in range(len(self.ranks_of_arm)):
+            src = self.leader(a)
+            if src == 0:
+                if self.rank == 0:
+                    got[a] = per_arm[a]
+                continue
+            if self.rank == 0:
+                dev = next(iter(per_arm.values()))[0].device if per_arm else torch.device("cpu")
+                got[a] = [torch.empty(shape, dtype=dtype, device=dev) for shape, dtype in like[a]]
+                ops += [dist.P2POp(dist.irecv, t, src) for t in got[a]]
+            elif self.rank == src:
+                ops += [dist.P2POp(dist.isend, t.contiguous(), 0) for t in per_arm[a]]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return got if self.rank == 0 else per_arm
 
 
 class RoadmapBuilder:
@@ -230,17 +301,16 @@ class RoadmapBuilder:
             idx[bad], dist[bad], amb[bad] = idx2, dist2, amb2
         self._mark("knn_rerank")
         if rows is not None:   # spatial slices -> the caller's row order, on every rank
+            # ONE all-gather of packed records (row id, flag, idx, fp64 dist: 128 B per row at k = 10)
+            # and ONE scatter kernel; padding records carry row id -1
             widest = max(b - a for a, b in zip(self.cuts[:-1], self.cuts[1:]))
             cap = (int(np.ceil(-(-n // 128) * widest)) + 2) * 128       # rows the widest slice can hold
-            at = all_gather_padded(rows, cap, self.size, self.group, fill=n).long()   # padding -> row n
-            tables = []
-            for part in (idx, dist, amb):
-                part = all_gather_padded(part, cap, self.size, self.group)
-                full = torch.empty((n + 1,) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
-                full.index_copy_(0, at, part)      # (11x faster than full[at] = part on fp64 rows)
-                tables.append(full[:n])
-            idx, dist, amb = tables
-            self._rebalance(t0.elapsed_time(t1))
+            rec = core.pack_neighbour_records(rows, idx, dist, amb, cap)
+            allrec = all_gather_padded(rec, cap, self.size, self.group)
+            idx, dist, amb = core.scatter_neighbour_records(allrec, self.k, n)
+            if self.size <= 4:          # the cuts only move up to 4 ranks (see _rebalance)
+                t1.synchronize()
+                self._rebalance(t0.elapsed_time(t1))
             self._mark("gather_adjacency")
         mine = idx[lo:hi].contiguous() if self.size > 1 else idx
         edges = core.edges_from_knn(mine)
@@ -258,11 +328,69 @@ class RoadmapBuilder:
                 idx, dist, amb = idx[lo:hi], dist[lo:hi], amb[lo:hi]
         return {"idx": idx, "dist": dist, "edge_free": free, "ambiguous": amb, "rows": (lo, hi) if not gather else (0, n)}
 
-    def build(self, n: int, seed: int):
+    def build(self, n: int, seed: int, k2: Optional[int] = None):
+        """Learning phase of one arm, device resident: samples -> candidate tables (k nearest +
+        edge verdicts); with k2 also the accepted adjacency and its components (adjacency())."""
         q64, q32 = self.sample_free(n, seed)
         out = self.candidates(q64, q32)
         out["q64"], out["q32"] = q64, q32
+        if k2 is not None:
+            self.adjacency(out, k2)
         return out
+
+    def adjacency(self, out, k2: Optional[int] = None, cap: Optional[int] = None):
+        """The roadmap itself: connect_nearest_neighbors_degree's accept pass (decoupled_prm.py:
+        496-503: nodes in id order, candidates in (dist, id) order, insert at both ends while both
+        hold fewer than k2 edges) on the gathered candidate tables, then its connected components
+        (:613-636).  Adds adj [n, cap] int32 (-1 padded, reference list order), deg [n],
+        labels [n], n_components ([1] int64, left on the device) to `out`."""
+        k2 = self.k if k2 is None else k2
+        out["adj"], out["deg"] = core.greedy_degree_connect_device(out["idx"], out["edge_free"], k2, cap)
+        self._mark("accept_pass")
+        out["labels"], out["n_components"] = core.connected_components(out["adj"], sync=False)
+        self._mark("components")
+        return out
+
+    def build_host(self, q_host: torch.Tensor, k2: int, pinned_out: Optional[dict] = None):
+        """The host-buffer build for a TEAM of ranks (one rank: SpatialWorld.roadmap_build_host, the
+        C-ABI call).  q_host [N, D] fp64 page-locked samples, the same on every rank of the team.
+        Every rank uploads and accept-tests only ITS row block, the free rows are all-gathered (node
+        ids = input order), the team shares neighbour search and edge checks, every rank runs the
+        accept pass and copies ITS row block of every table back into page-locked buffers.
+        -> dict of host tensors for rows [lo, hi) of the n nodes: node_src, nbr_idx, nbr_dist,
+        edge_free, adj, deg, labels; plus n_nodes, rows."""
+        N = q_host.shape[0]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        a, b = shard_rows(N, self.rank, self.size)
+        mine = q_host[a:b].to(dev, non_blocking=True)
+        m32 = core.pack_f32(mine)
+        hit = self.world.collide_configs(m32, self.robot, self.flags)
+        keep = core.compact_free(hit)
+        src = keep + a
+        q64 = all_gather_rows(core.gather_rows(mine, keep), self.size, self.group)
+        src = all_gather_rows(src[:, None].contiguous(), self.size, self.group)[:, 0].contiguous()
+        q32 = core.pack_f32(q64)
+        self._mark("h2d_accept_gather")
+        out = self.candidates(q64, q32)
+        self.adjacency(out, k2)
+        n = q64.shape[0]
+        lo, hi = shard_rows(n, self.rank, self.size)
+        host = pinned_out if pinned_out is not None else {}
+        tables = {"node_src": src, "nbr_idx": out["idx"], "nbr_dist": out["dist"], "edge_free": out["edge_free"],
+                  "adj": out["adj"], "deg": out["deg"], "labels": out["labels"]}
+        res = {}
+        for key, t in tables.items():
+            part = t[lo:hi]
+            buf = host.get(key)
+            if buf is None or buf.shape[0] < hi - lo or buf.shape[1:] != part.shape[1:] or buf.dtype != part.dtype:
+                buf = torch.empty((hi - lo,) + tuple(part.shape[1:]), dtype=part.dtype, pin_memory=True)
+                host[key] = buf
+            buf[: hi - lo].copy_(part, non_blocking=True)
+            res[key] = buf[: hi - lo]
+        torch.cuda.current_stream().synchronize()
+        self._mark("d2h")
+        res.update(n_nodes=n, rows=(lo, hi))
+        return res
 
     def components(self, out):
         """Connected components of the collision-free candidate graph of build() / candidates()

@@ -14,10 +14,12 @@
  * between convex hulls of point sets (optionally inflated by a radius =
  * Bullet's collision margin / a sphere or capsule primitive).
  *
- * PARITY UNPINNED: no pybullet in the build container and none of the
- * reference's tests records a collision verdict, so this oracle is pinned only
- * by its own known-answer tests (tests/test_oracle_hull.py), not by reference
- * output.
+ * PARITY UNPINNED: no pybullet in the build container nor on the GPU box
+ * (probed: profiles/r02_pybullet_probe.txt) and none of the reference's tests
+ * records a collision verdict, so this oracle is pinned only by known answers and
+ * by an independent algorithm (LP feasibility / QP distance on the real Panda
+ * hulls): tests/test_oracle_cpu.py::test_hull_oracle_known_answers and
+ * ::test_hull_oracle_vs_linear_programming -- not by reference output.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
  * call this code.

@@ -1,5 +1,5 @@
 """bench.py contract pieces that need no GPU: the reference arm (the oracle port on the host
-cores -- one of the places allowed to execute oracle/), the ncu traffic reader, and the rule
+cores -- one of the places allowed to execute oracle/), the profile readers, the arm layout, and the rule
 that the product arm fails loudly without a CUDA device instead of falling back."""
 import json
 import os
@@ -31,12 +31,35 @@ def test_reference_arm_other_ranks_do_nothing():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_ncu_traffic_reader():
+def test_kernel_flops_arithmetic_and_missing_profile():
+    """tools/kernel_flops.py: the FP32 work of a launch is 2*(FFMA + 2*FFMA2) + FADD + 2*FADD2 + FMUL + 2*FMUL2
+    thread-level instructions; bench.py reads the per-unit figures from profiles/ and degrades to
+    null fractions, not to invented ones, when the file is missing."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench
+    import kernel_flops
+    launch = {f"sm__sass_thread_inst_executed_op_{n}_pred_on.sum": (str(v), "inst")
+              for n, v in (("ffma", 100), ("ffma2", 10), ("fadd", 7), ("fadd2", 1), ("fmul", 5), ("fmul2", 2))}
+    assert kernel_flops.fp32_flop(launch) == 2 * (100 + 20) + 7 + 2 + 5 + 4
+    assert kernel_flops.num({"dram__bytes_read.sum": ("1.5", "Mbyte")}, "dram__bytes_read.sum") == 1.5e6
+    assert bench.load_json(os.path.join(ROOT, "profiles", "no_such_file.json"), {}) == {}
+
+
+def test_arm_layout_and_csv_row():
     sys.path.insert(0, ROOT)
     import bench
-    t = bench.ncu_traffic(os.path.join(ROOT, "profiles", "r01_knn_scan_full.csv"))
-    assert isinstance(t, int) and 1e8 < t < 1e10          # ~0.4 GB per launch: the packed rows stay in L2
-    assert bench.ncu_traffic(os.path.join(ROOT, "profiles", "no_such_file.csv")) is None
+    from mmmp_b200.roadmap import arm_layout
+    assert arm_layout(1, 4) == [[0]] * 4
+    assert arm_layout(2, 4) == [[0], [1], [0], [1]]
+    assert arm_layout(4, 4) == [[0], [1], [2], [3]]
+    assert arm_layout(8, 4) == [[0, 1], [2, 3], [4, 5], [6, 7]]
+    assert arm_layout(6, 4) == [list(range(6))] * 4          # no even split: every arm over all ranks
+    for ws in (1, 2, 3, 4, 8, 16):                           # every rank has work, every arm an owner
+        lay = arm_layout(ws, 4)
+        assert set(r for ranks in lay for r in ranks) == set(range(ws))
+    row = bench.csv_row(0.25, 1000, 9000, 0.6)
+    assert row == {"learning_time": 0.25, "n_nodes": 1000, "n_edges": 4500, "avg_degree": 9.0, "max_edge_len": 0.6}
 
 
 def test_product_arm_fails_loudly_without_a_gpu():

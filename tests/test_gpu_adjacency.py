@@ -1,0 +1,131 @@
+"""Roadmap build up to the adjacency on the device: the degree-capped greedy
+accept pass of connect_nearest_neighbors_degree (decoupled_prm.py:496-503) as data-parallel
+rounds (csrc/greedy.cu), against
+
+  * the oracle's sequential restatement oracle/knn.greedy_degree (pinned by the reference's own
+    production method run unbound, tests/golden/panda_heap_knn.npz and the 12-node known answer),
+  * the native host replay mmmp_greedy_degree_connect (already pinned the same way),
+
+bit for bit: same edges AND same order inside every adjacency list (the order decides what the
+Python planners' edge_dicts lists look like).  Then the whole build of one C5 arm -- candidates ->
+accept pass -> connected components -- at 1 M nodes against the host replay and a host union-find.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def core(cuda):
+    from mmmp_b200 import core
+    return core
+
+
+def _oracle_adj(idx, free, k2, cap):
+    """oracle/knn.greedy_degree restated on a candidate TABLE (holes, self references and
+    duplicates inside a row are visited in turn, as the reference's loop would visit a list)."""
+    n, k1 = idx.shape
+    adj = [[] for _ in range(n)]
+    for i in range(n):
+        for c in range(k1):
+            j = int(idx[i, c])
+            if len(adj[i]) == k2:
+                break
+            if j < 0 or j >= n or j == i:
+                continue
+            if free[i, c] and j not in adj[i] and len(adj[j]) != k2:
+                adj[i].append(j)
+                adj[j].append(i)
+    out = np.full((n, cap), -1, np.int32)
+    for i, a in enumerate(adj):
+        out[i, :len(a)] = a
+    return out
+
+
+@pytest.mark.parametrize("n,k1,k2,pfree", [(1, 3, 2, 1.0), (2, 1, 1, 1.0), (7, 4, 2, 0.8), (500, 10, 10, 0.75),
+                                           (500, 10, 3, 1.0), (3000, 16, 6, 0.5), (3000, 5, 1, 0.9),
+                                           (20000, 10, 10, 0.75), (20000, 10, 4, 1.0)])
+def test_greedy_rounds_equal_sequential_pass(core, cuda, n, k1, k2, pfree):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(n * 31 + k1 * 7 + k2)
+    X = rng.random((n, 4))
+    kk = min(k1 + 1, n)
+    _, nb = cKDTree(X).query(X, k=kk)
+    nb = nb.reshape(n, kk)
+    idx = np.full((n, k1), -1, np.int32)
+    idx[:, :kk - 1] = nb[:, 1:]
+    free = (rng.random((n, k1)) < pfree).astype(np.uint8)
+    if n >= 500:      # hostile rows: duplicates, self references, holes, out-of-range ids
+        r = rng.choice(n, 40, replace=False)
+        idx[r[:10], 3] = idx[r[:10], 1]
+        idx[r[10:20], 2] = r[10:20]
+        idx[r[20:30], 0] = -1
+        idx[r[30:], 1] = n + 5
+    cap = k2 + 2
+    adj, deg, rounds = core.greedy_degree_connect_device(torch.from_numpy(idx).to(cuda), torch.from_numpy(free).to(cuda),
+                                                         k2, cap, return_rounds=True)
+    adj, deg = _np(adj), _np(deg)
+    ref = _oracle_adj(idx, free, k2, cap)
+    assert (adj == ref).all(), f"adjacency differs from the sequential pass in {(adj != ref).any(1).sum()} rows"
+    assert (deg == (ref >= 0).sum(1)).all() and deg.max(initial=0) <= k2
+    host_adj, host_deg = core.greedy_degree_connect(idx, free, k2, cap)
+    assert (host_adj == adj).all() and (host_deg == deg).all()
+    assert 1 <= rounds < 200
+
+
+def test_greedy_matches_reference_golden(core, golden, cuda):
+    """The reference's own connect_nearest_neighbors_degree output (production method run unbound
+    on 300 Panda samples, tools/gen_golden.py): candidates from the golden k-NN table, all
+    edges free."""
+    g = golden("panda_heap_knn")
+    idx = g["l2_knn_idx"].astype(np.int32)
+    free = np.ones_like(idx, dtype=np.uint8)
+    for k2 in (3, 6, 10):
+        adj, deg = core.greedy_degree_connect_device(torch.from_numpy(idx).to(cuda), torch.from_numpy(free).to(cuda), k2)
+        assert (_np(adj) == _oracle_adj(idx, free, k2, k2)).all()
+
+
+def test_build_to_adjacency_1m(core, cuda):
+    """One C5 arm, 1 M nodes: candidates -> accept pass -> components, all on the device; the
+    adjacency equals the native host replay of the reference loop and the component labels
+    equal a host union-find over the accepted edges."""
+    import time
+    from mmmp_b200.roadmap import RoadmapBuilder
+    model = core.load_model("panda_spheres")
+    base = core.base_matrix((0.665, 0, 0.01), (0, 0, 1, 0))
+    world = core.SpatialWorld([core.RobotSpec(model, base)], [core.plane((0, 0, 1), 0.0)])
+    n = 1_000_000
+    b = RoadmapBuilder(world, 0, "fk", 10, 50, 0.02, single_rank=True)
+    out = b.build(n, seed=3)
+    for k2 in (10, 6):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        adj, deg, rounds = core.greedy_degree_connect_device(out["idx"], out["edge_free"], k2, return_rounds=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_adj, host_deg = core.greedy_degree_connect(_np(out["idx"]), _np(out["edge_free"]), k2)
+        host_ms = (time.perf_counter() - t0) * 1e3
+        print(f"accept pass 1M x 10, k2={k2}: device {e0.elapsed_time(e1):.2f} ms in {rounds} rounds, "
+              f"host replay {host_ms:.1f} ms, mean degree {float(deg.float().mean()):.3f}")
+        assert (_np(adj) == host_adj).all() and (_np(deg) == host_deg).all()
+    labels, count = core.connected_components(adj)
+    # host union-find over the accepted edges
+    a = _np(adj)
+    src = np.repeat(np.arange(n), a.shape[1])[a.ravel() >= 0]
+    dst = a.ravel()[a.ravel() >= 0]
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    ncomp, lab = connected_components(coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n, n)), directed=False)
+    assert ncomp == count
+    first = np.full(ncomp, n, np.int64)
+    np.minimum.at(first, lab, np.arange(n))
+    assert (_np(labels) == first[lab]).all()
+    world.close()

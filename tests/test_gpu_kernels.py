@@ -240,6 +240,63 @@ def test_edge_step_skipping_keeps_every_verdict(core, panda_model, cuda):
         assert 0.02 < full.mean() < 0.98
 
 
+def test_capsule_cull_keeps_every_verdict(core, panda_model, cuda):
+    """Between a link pair's bounding spheres and its sphere sets the kernels test the links'
+    bounding CAPSULES (fitted at world creation).  The capsules contain every sphere of their
+    link, so the cull can only skip descents that would not have hit: verdicts with and without
+    the stage (MMMP_CHECK_NO_CAPSULES) are identical -- 2 M single-arm configurations, 400 k
+    two-arm composite rows (robot-robot pairs), KUKA, and 200 k edges through the step-skipping
+    and the exhaustive kernels (whose clearances the capsules change, but not their OR)."""
+    from mmmp_b200._lib import CHECK_EXHAUSTIVE, CHECK_NO_CAPSULES, CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_SELF
+    NC = CHECK_NO_CAPSULES
+    lim = np.array(panda_model["joint_limits"])
+    w = core.SpatialWorld([core.RobotSpec(panda_model, core.base_matrix((0, 0, 0.01)))], _scene(core))
+    q64, q32 = core.sample_uniform(lim[:, 0], lim[:, 1], 2_000_000, seed=99)
+    for flags in (CHECK_SELF, CHECK_SELF | CHECK_OBSTACLES):
+        a, b = w.collide_configs(q32, 0, flags), w.collide_configs(q32, 0, flags | NC)
+        assert torch.equal(a, b), int((a != b).sum())
+        assert 0.05 < float(a.float().mean()) < 0.6
+    # the plain sphere model, without the offline pair tables / proven pairs: every self pair goes
+    # through the capsule stage
+    wp = core.SpatialWorld([core.RobotSpec(panda_model, core.base_matrix((0, 0, 0.01)), use_pair_tables=False)], [])
+    a, b = wp.collide_configs(q32, 0, CHECK_SELF), wp.collide_configs(q32, 0, CHECK_SELF | NC)
+    assert torch.equal(a, b), int((a != b).sum())
+    # edges: roadmap-like short edges and long ones
+    rng = np.random.default_rng(5)
+    n = 200_000
+    qa = _np(q64[:n])
+    sigma = rng.choice([0.02, 0.1, 0.3, 1.0], size=(n, 1))
+    qb = np.clip(np.round(qa + rng.normal(0, 1.0, qa.shape) * sigma, 2), lim[:, 0], lim[:, 1])
+    a32, b32 = q32[:n].contiguous(), core.pack_f32(core.to_device_f64(qb))
+    F = CHECK_SELF | CHECK_OBSTACLES
+    ref = w.collide_segments(a32, b32, 50, 0.02, 0, F | NC | CHECK_EXHAUSTIVE)
+    for flags in (F, F | CHECK_EXHAUSTIVE, F | NC):
+        got = w.collide_segments(a32, b32, 50, 0.02, 0, flags)
+        assert torch.equal(got, ref), (flags, int((got != ref).sum()))
+    assert 0.05 < float(ref.float().mean()) < 0.95
+    # two arms close together: robot-robot link pairs
+    bases = [core.base_matrix((-0.35, 0, 0.01)), core.base_matrix((0.35, 0, 0.01), (0, 0, 1, 0))]
+    w2 = core.SpatialWorld([core.RobotSpec(panda_model, bases[0], 0), core.RobotSpec(panda_model, bases[1], 7)],
+                           [core.plane((0, 0, 1), 0.0)])
+    c64, c32 = core.sample_uniform(np.tile(lim[:, 0], 2), np.tile(lim[:, 1], 2), 400_000, seed=3)
+    for flags in (CHECK_ROBOTS, CHECK_SELF | CHECK_OBSTACLES | CHECK_ROBOTS):
+        a, b = w2.collide_configs(c32, -1, flags), w2.collide_configs(c32, -1, flags | NC)
+        assert torch.equal(a, b), int((a != b).sum())
+        assert 0.05 < float(a.float().mean()) < 0.95
+    m = 40_000
+    ea, eb = c32[:m].contiguous(), c32[m:2 * m].contiguous()
+    FR = CHECK_SELF | CHECK_OBSTACLES | CHECK_ROBOTS
+    ref = w2.collide_segments(ea, eb, 20, 0.05, -1, FR | NC | CHECK_EXHAUSTIVE)
+    assert torch.equal(w2.collide_segments(ea, eb, 20, 0.05, -1, FR), ref)
+    # KUKA iiwa14 (the reference's own sphere URDF)
+    km = core.load_model("kuka_iiwa14_spheres")
+    klim = np.array(km["joint_limits"])
+    wk = core.SpatialWorld([core.RobotSpec(km, core.base_matrix((0, 0, 0.0)))], [core.plane((0, 0, 1), -0.02)])
+    k64, k32 = core.sample_uniform(klim[:, 0], klim[:, 1], 500_000, seed=4)
+    a, b = wk.collide_configs(k32, 0, F), wk.collide_configs(k32, 0, F | NC)
+    assert torch.equal(a, b) and 0.02 < float(a.float().mean()) < 0.98
+
+
 def test_two_pandas_composite_and_pairs_vs_sphere_oracle(core, panda_model, cuda):
     from mmmp_b200._lib import CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_SELF
     from oracle.spheres import SphereChecker
@@ -280,7 +337,9 @@ def test_sphere_model_is_conservative_vs_hull_oracle(core, panda_model, cuda):
         false_neg = (ref & ~got).sum()
         false_pos = (~ref & got).mean()
         assert false_neg == 0, f"sphere model missed {false_neg} hull collisions (flags={flags})"
-        assert false_pos < 0.25
+        # measured 3.6 % for the whole accept test on 20 000 configurations (profiles/r01_disagreement.txt:
+        # self 2.5 %, obstacles 2.0 %); 4000 samples: 3 sigma of sampling noise on top
+        assert false_pos < 0.05
 
 
 # --------------------------------------------------------------------- (d) neighbour search

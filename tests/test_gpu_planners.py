@@ -441,3 +441,138 @@ def test_task_space_sampler(cuda, golden):
 def core_base(model):
     from mmmp_b200 import core
     return core.base_matrix(model.base_position, model.base_orientation)
+
+
+def test_start_goal_poses_are_sampled_in_task_space(cuda):
+    """sample_start_poses / sample_goal_poses (decoupled_prm.py:438-470): tool positions drawn
+    around the start / goal TOOL position (three normals per sample from numpy's global stream,
+    sigma 0.2 m), closest IK from the start / goal pose with the tool pointing down.  The draws are
+    the reference's; the joint values are pinned against the float64 restatement of the solver."""
+    from mmmp_b200.planners.prm.pybullet.decoupled.decoupled_prm import DecoupledPRM
+    from oracle import ik
+    env = _panda_env(1)
+    prm = DecoupledPRM(env, maxdist=0, k1=4, k2=3, build_type='n', prm_type='degree', n=1, t=1, time_step=0.1,
+                       local_step=0.05)
+    r_id, model = prm.r_ids[0], prm.robot_models[0]
+    base = core_base(model)
+    for which, fn in (("start", prm.sample_start_poses), ("goal", prm.sample_goal_poses)):
+        pose = np.asarray(env.agents[0][which], dtype=float)[:7]
+        np.random.seed(11)
+        got = np.array(fn(r_id, n=10))
+        after = np.random.get_state()[1].tolist()
+        np.random.seed(11)
+        pos0 = model.position_from_fk(pose)
+        want = np.array([[pos0[0] + np.random.normal(0, 0.2), pos0[1] + np.random.normal(0, 0.2),
+                          pos0[2] + np.random.normal(0, 0.2)] for _ in range(10)])
+        assert np.random.get_state()[1].tolist() == after            # same number of draws, same order
+        q_ref, ok, _ = ik.ik_dls(model.model, base, want, np.tile([[1.0, 0, 0, 0]], (10, 1)), np.tile(pose, (10, 1)))
+        assert got.shape == (10, 7) and ok.sum() >= 5
+        assert np.abs(got - q_ref)[ok].max() < 2e-3
+        tool = np.array([model.position_from_fk(q) for q in got])
+        assert np.linalg.norm(tool - want, axis=1)[ok].max() < 1e-3
+        lo = np.array([iv.lower for iv in prm.c_spaces[0]])
+        hi = np.array([iv.upper for iv in prm.c_spaces[0]])
+        assert ((got >= lo - 1e-6) & (got <= hi + 1e-6)).all()
+
+
+def test_prioritized_prm_paths_are_collision_free_under_hull_oracle(cuda):
+    """The Prioritized-PRM drop-in class (prioritized_prm.py:14-49,113-168): two Panda roadmaps built
+    on the GPU, robots planned in priority order on the host, the per-edge robot-robot sweep of
+    robot_robot_collision_on_edge answered by the batched pair kernel.  Every discretised
+    configuration of the returned paths is re-validated with the hull oracle (self, ground plane,
+    robot-robot at the planner's own time grid), and the batched sweep is compared with the hull
+    oracle's verdicts edge by edge (conservative: it may only ADD collisions)."""
+    from mmmp_b200 import core
+    from mmmp_b200.planners.prm.pybullet.decoupled.prioritized_prm import PrioritizedPRM
+    from oracle.hull import PandaHullChecker
+    env = _panda_env(2)
+    prm = PrioritizedPRM(env, load_roadmap=None, maxdist=0.1, k1=12, k2=8, build_type='n', prm_type='degree', n=400, t=0,
+                         time_step=0.1, local_step=0.02, seed=5)
+    assert prm.compute_combined_nr_nodes() == 2 * (400 + 49)
+    res = prm.query()
+    assert res, "Prioritized-PRM found no solution"
+    paths, l_t, q_t = res
+    assert set(paths) == set(prm.r_ids) and l_t >= 0 and q_t >= 0
+    for r_id, path in paths.items():
+        assert path[0] == -1 and path[-1] == -2                         # start and goal node ids (decoupled_prm.py:943-995)
+        ed = prm.edge_dicts[prm.r_ids.index(r_id)]
+        assert all(b in ed[a] for a, b in zip(path[:-1], path[1:]))      # a walk on the roadmap
+    # default priorities [1, 2]: np.argsort(...)[::-1] plans the LAST robot first (prioritized_prm.py:55-60)
+    bases = [m.base_matrix for m in env.robot_models]
+    hull = PandaHullChecker(bases, [core.plane((0, 0, 1), 0.0)])
+    st = {r: prm.discretize_path_in_time(r, paths[r]) for r in paths}
+    for r_index, r_id in enumerate(prm.r_ids):
+        q = np.array([np.asarray(v, float) for v in st[r_id].values()])
+        assert not hull.config_collision(q, r_index).any()
+    t_max = max(max(p.keys()) for p in st.values())
+    qa, qb = [], []
+    for t in np.round(np.arange(0, t_max, prm.time_step), 1):
+        pa, pb = st[prm.r_ids[0]], st[prm.r_ids[1]]
+        qa.append(pa[min(pa.keys(), key=lambda x: abs(x - t))])
+        qb.append(pb[min(pb.keys(), key=lambda x: abs(x - t))])
+    assert not hull.robot_robot_collision(np.array(qa, float), np.array(qb, float), 0, 1).any()
+    # robot_robot_collision_on_edge against the hull oracle on roadmap edges of robot 0 while robot 1
+    # follows its path: never misses a hull collision
+    r0, r1 = prm.r_ids
+    ed = prm.edge_dicts[0]
+    rng = np.random.default_rng(3)
+    nodes = [n for n in ed if n >= 0 and ed[n]]
+    missed = checked = 0
+    for a in rng.choice(nodes, 40, replace=False):
+        b = ed[a][0]
+        start_time = float(rng.uniform(0, max(t_max - 1.0, 0.1)))
+        got = prm.robot_robot_collision_on_edge(a, b, r0, {r1: st[r1]}, start_time)
+        qa_, qb_ = np.array(prm.node_id_q_dicts[0][a]), np.array(prm.node_id_q_dicts[0][b])
+        dt = np.linalg.norm(qa_ - qb_) / prm.local_step * prm.time_step
+        t0 = np.round(np.ceil(start_time / prm.time_step) * prm.time_step, 1)
+        t1 = np.round(np.floor((start_time + dt) / prm.time_step) * prm.time_step, 1)
+        times = [np.round(t, 1) for t in np.arange(t0, t1 + prm.time_step, prm.time_step)]
+        if not times:
+            assert got is False
+            continue
+        mine = np.array([prm.find_q_in_q_t_interval_given_t(np.append(qa_, start_time), np.append(qb_, start_time + dt), t)
+                         for t in times], float)[:, :7]
+        keys = np.array(list(st[r1].keys()))
+        vals = list(st[r1].values())
+        theirs = np.array([np.asarray(vals[j], float) for j in np.abs(keys[None] - np.array(times)[:, None]).argmin(1)])
+        ref = bool(hull.robot_robot_collision(mine, theirs, 0, 1).any())
+        checked += 1
+        missed += int(ref and not got)
+    assert checked >= 10 and missed == 0
+
+
+def test_kuka_collision_vs_sphere_oracle(cuda):
+    """KUKA iiwa14 (the chain north_star names beside the Panda): configuration and edge collision of
+    the reference's own sphere URDF (models/kuka_iiwa/urdf/iiwa14_spheres_collision.urdf) against the
+    float64 sphere oracle -- self, obstacles, and two KUKAs against each other."""
+    from mmmp_b200 import core
+    from mmmp_b200._lib import CHECK_OBSTACLES, CHECK_ROBOTS, CHECK_SELF
+    from oracle.spheres import SphereChecker
+    m = core.load_model("kuka_iiwa14_spheres")
+    lim = np.array(m["joint_limits"])
+    rng = np.random.default_rng(8)
+    bases = [core.base_matrix((0, 0, 0.0)), core.base_matrix((0.6, 0.1, 0.0), (0, 0, 1, 0))]
+    obs = [core.plane((0, 0, 1), -0.02), core.box((0.45, 0.0, 0.4), (0.08, 0.3, 0.1)), core.sphere((-0.3, 0.3, 0.7), 0.15)]
+    w1 = core.SpatialWorld([core.RobotSpec(m, bases[0])], obs)
+    ck1 = SphereChecker([m], [bases[0]], obs)
+    q = np.round(rng.uniform(lim[:, 0], lim[:, 1], (4000, 7)), 2)
+    q32 = core.pack_f32(core.to_device_f64(q))
+    for flags, ref in ((CHECK_SELF, ck1.config_collision(q, 0, obstacles=False)),
+                       (CHECK_OBSTACLES, ck1.config_collision(q, 0, self_=False)),
+                       (CHECK_SELF | CHECK_OBSTACLES, ck1.config_collision(q, 0))):
+        got = w1.collide_configs(q32, 0, flags).cpu().numpy().astype(bool)
+        assert (got != ref).sum() <= 3, (flags, int((got != ref).sum()))
+    full = ck1.config_collision(q, 0)
+    assert 0.02 < full.mean() < 0.98
+    free = np.nonzero(~full)[0]
+    ea, eb = rng.choice(free, 300), rng.choice(free, 300)
+    edges = torch.tensor(np.stack([ea, eb], 1), dtype=torch.int32, device=cuda)
+    got = w1.collide_edges(q32, edges, 20, 0.05, 0, CHECK_SELF | CHECK_OBSTACLES).cpu().numpy().astype(bool)
+    ref = ck1.edge_collision(q[ea], q[eb], 20, 0.05, 0)
+    assert (got != ref).sum() <= 3 and 0.05 < ref.mean() < 0.95
+    w2 = core.SpatialWorld([core.RobotSpec(m, bases[0], 0), core.RobotSpec(m, bases[1], 7)], obs)
+    ck2 = SphereChecker([m, m], bases, obs)
+    qq = np.round(rng.uniform(np.tile(lim[:, 0], 2), np.tile(lim[:, 1], 2), (1500, 14)), 2)
+    got = w2.collide_configs(core.pack_f32(core.to_device_f64(qq)), -1, CHECK_ROBOTS).cpu().numpy().astype(bool)
+    ref = ck2.robot_robot_collision(qq[:, :7], qq[:, 7:], 0, 1)
+    assert (got != ref).sum() <= 2 and 0.02 < ref.mean() < 0.98

@@ -152,6 +152,53 @@ def test_hull_oracle_known_answers():
     assert not hull.PandaHullChecker([core.base_matrix((0, 0, 0.01))]).self_collision(q)[0]
 
 
+def test_hull_oracle_vs_linear_programming():
+    """An independent algorithm for the same question (pybullet itself is absent on the build and the
+    GPU box: profiles/r02_pybullet_probe.txt): two convex hulls intersect iff the LP
+    { lambda, mu >= 0, sum lambda = sum mu = 1, A^T lambda = B^T mu } is feasible (scipy HiGHS), and
+    their distance is the optimum of the QP min |A^T lambda - B^T mu| (SLSQP).  The GJK oracle must
+    give the same verdicts and distances on the real Panda link hulls in random relative poses."""
+    from scipy.optimize import linprog, minimize
+    from mmmp_b200 import core
+    from oracle import hull
+    H = hull.hulls()
+    rng = np.random.default_rng(12)
+    pairs = [(1, 5), (2, 5), (5, 7), (2, 6), (0, 7), (1, 6), (3, 8), (4, 9)]
+    n_hit = n_checked = 0
+    for n in range(48):
+        la, lb = pairs[n % len(pairs)]
+        # link lb in a random pose around link la: random rotation, centroids 0 .. 0.3 m apart
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        Q *= np.sign(np.linalg.det(Q))
+        u = rng.normal(size=3)
+        TA, TB = np.eye(4), np.eye(4)
+        TB[:3, :3] = Q
+        TB[:3, 3] = H[la].mean(0) + u / np.linalg.norm(u) * rng.uniform(0.0, 0.3) - Q @ H[lb].mean(0)
+        A = H[la] @ TA[:3, :3].T + TA[:3, 3]
+        B = H[lb] @ TB[:3, :3].T + TB[:3, 3]
+        d = hull.posed_distance(H[la], TA[None], H[lb], TB[None])[0]
+        na, nb = len(A), len(B)
+        Aeq = np.zeros((5, na + nb))
+        Aeq[:3, :na], Aeq[:3, na:] = A.T, -B.T
+        Aeq[3, :na] = 1
+        Aeq[4, na:] = 1
+        lp = linprog(np.zeros(na + nb), A_eq=Aeq, b_eq=[0, 0, 0, 1, 1], bounds=(0, None), method="highs")
+        feasible = lp.status == 0
+        if abs(d) > 1e-6 or feasible:                      # (a grazing contact may be either for the LP)
+            assert feasible == (d <= 0.0), (n, la, lb, d, lp.status)
+        n_hit += int(d <= 0.0)
+        if d > 1e-3 and n_checked < 5:                    # distance by an independent QP on a few separated pairs
+            x0 = np.concatenate([np.full(na, 1 / na), np.full(nb, 1 / nb)])
+            res = minimize(lambda x: ((x[:na] @ A - x[na:] @ B) ** 2).sum(), x0, method="SLSQP",
+                           jac=lambda x: np.concatenate([2 * A @ (x[:na] @ A - x[na:] @ B), -2 * B @ (x[:na] @ A - x[na:] @ B)]),
+                           bounds=[(0, 1)] * (na + nb), options={"maxiter": 400, "ftol": 1e-14},
+                           constraints=[{"type": "eq", "fun": lambda x: x[:na].sum() - 1},
+                                        {"type": "eq", "fun": lambda x: x[na:].sum() - 1}])
+            assert np.sqrt(res.fun) == pytest.approx(d, abs=2e-4), (n, la, lb)
+            n_checked += 1
+    assert 8 <= n_hit <= 40 and n_checked >= 4
+
+
 def test_task_space_position_sampler_matches_reference(golden):
     """oracle.ik.task_space_positions restates sample_task_space_position (decoupled_prm.py:346-369);
     golden = the reference's own function under a seeded numpy stream + the draws it consumed."""

@@ -71,6 +71,21 @@ def _worker(rank, size, port, out):
         allf = all_gather_rows(torch.from_numpy(free), size).numpy()
         single = sampling.sample_uniform(lo_, hi_, per * size, seed, first)
         ok &= bool((allf == single[single[:, 0] > -1.0]).all())
+        # arm-parallel layout: 4 arms on 2 ranks -> rank r builds arms r and r + 2 alone; the
+        # hand-over leaves every arm's tables on rank 0
+        from mmmp_b200.roadmap import ArmTeams
+        teams = ArmTeams(4)
+        ok &= teams.my_arms == [rank, rank + 2] and teams.team(rank) == (None, True) and teams.leader(3) == 1
+        mine = {a: [torch.full((5, 3), a, dtype=torch.int32), torch.arange(5, dtype=torch.int32) + 10 * a]
+                for a in teams.my_arms}
+        like = {a: [((5, 3), torch.int32), ((5,), torch.int32)] for a in range(4)}
+        got = teams.collect_on_root(mine, like)
+        if rank == 0:
+            ok &= sorted(got) == [0, 1, 2, 3]
+            ok &= all(bool((got[a][0] == a).all()) and bool((got[a][1] == torch.arange(5) + 10 * a).all()) for a in range(4))
+        # one arm on 2 ranks: the team is the whole world (sharded build inside the team)
+        one = ArmTeams(1)
+        ok &= one.ranks_of_arm == [[0, 1]] and one.team(0) == (None, False) and one.my_arms == [0]
         out[rank] = ok
     finally:
         dist.destroy_process_group()
