@@ -36,6 +36,24 @@ namespace {
 #define MMMP_EDGE_DEFER_ROUNDS 2    // rounds after which an edge may still be handed to the second pass
 #endif
 
+#ifdef MMMP_EDGE_DIAG
+// tuning aid (variant builds only, tools/edge_diag.py): which clearance term limited an evaluation
+// that proved less than `g_diag_steps` steps.  [0..7] obstacle term of joint j, [16+pi] self pair
+// pi, [32+n] evaluations that proved n steps per side (n capped at 15), [63] evaluations.
+__device__ unsigned long long g_diag[64];
+__device__ float g_diag_spt = 50.f;
+#define MMMP_DIAG_MIN(expr, id)            \
+    do {                                   \
+        const float _t = (expr);           \
+        if (_t < tsafe) {                  \
+            tsafe = _t;                    \
+            why = (id);                    \
+        }                                  \
+    } while (0)
+#else
+#define MMMP_DIAG_MIN(expr, id) tsafe = fminf(tsafe, (expr))
+#endif
+
 struct SpatialSmem {
     int n_r;
     int n_obs;
@@ -220,14 +238,9 @@ __device__ __forceinline__ void capsule_pair(const RobotDev& RA, int la, const A
     const float denom = fmaf(a, e, -b * b);
     const float inv_a = __fdividef(1.f, fmaxf(a, 1e-20f)), inv_e = __fdividef(1.f, fmaxf(e, 1e-20f));
     float sp = denom > 1e-7f * a * e ? __saturatef(__fdividef(fmaf(b, f, -c * e), denom)) : 0.f;
-    float tp = fmaf(b, sp, f) * inv_e;
-    if (tp < 0.f) {
-        tp = 0.f;
-        sp = __saturatef(-c * inv_a);
-    } else if (tp > 1.f) {
-        tp = 1.f;
-        sp = __saturatef((b - c) * inv_a);
-    }
+    const float tp = __saturatef(fmaf(b, sp, f) * inv_e);   // closest point of segment 2 to P(sp) ...
+    sp = __saturatef(fmaf(b, tp, -c) * inv_a);              // ... and of segment 1 to Q(tp): covers Ericson's
+                                                            // clamp cases and degenerate (point) segments
     const float ex = fmaf(sp, d1x, rx) - tp * d2x, ey = fmaf(sp, d1y, ry) - tp * d2y, ez = fmaf(sp, d1z, rz) - tp * d2z;
     d2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
     rr = a0.w + b0.w;
@@ -303,6 +316,9 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
     float* cen = fr + (size_t)hdr->slots * 12 * stride;
     float* vel = cen + (size_t)hdr->links * 3 * stride;
     float tsafe = INF;
+#ifdef MMMP_EDGE_DIAG
+    int why = 30;
+#endif
     for (int lr = 0; lr < n_r; ++lr) {
         const RobotDev& R = robs[lr];
         const int col = hdr->col[lr];
@@ -383,7 +399,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                     if (hit) return HIT;
                 }
             }
-            if (GAP && n_obs > 0) tsafe = fminf(tsafe, (gmin - MMMP_GAP_SLACK) * inv_v);
+            if (GAP && n_obs > 0) MMMP_DIAG_MIN((gmin - MMMP_GAP_SLACK) * inv_v, j);
         }
         if (flags & MMMP_CHECK_SELF) {
             if (!skip_tables && tables_hit(Wg, R, lr, col, ql)) return HIT;
@@ -412,7 +428,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                     load_frame(TB, fr, stride, slot0, R.frame_store[mode][fb]);
                     if (link_pair_refine<GAP>(R, pr.x, TA, R, pr.y, TB, capsules, want, g)) return HIT;
                 }
-                if (GAP) tsafe = fminf(tsafe, __fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)));
+                if (GAP) MMMP_DIAG_MIN(__fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)), 16 + pi);
             }
         }
     }
@@ -454,13 +470,21 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                             load_frame(TB, fr, stride, hdr->frame_slot[l2], R2.frame_store[mode][fb]);
                             if (link_pair_refine<GAP>(R1, la, TA, R2, lb, TB, capsules, want, g)) return HIT;
                         }
-                        if (GAP) tsafe = fminf(tsafe, __fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)));
+                        if (GAP) MMMP_DIAG_MIN(__fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)), 31);
                     }
                 }
             }
         }
     }
     if (!GAP) return 1.f;
+#ifdef MMMP_EDGE_DIAG
+    {
+        const int n = (int)fminf(fmaxf(tsafe, 0.f) * g_diag_spt, 15.f);
+        atomicAdd(g_diag + 32 + n, 1ull);
+        atomicAdd(g_diag + 63, 1ull);
+        if (n < 1) atomicAdd(g_diag + why, 1ull);
+    }
+#endif
     return fmaxf(tsafe, 0.f);
 }
 
@@ -552,11 +576,43 @@ collide_edges_kernel(SpatialArgs A, const float* __restrict__ qa_base, const flo
     }
 }
 
+// position of the r-th (0-based) set bit of m, r < popcount(m): six popcount halvings (the __fns
+// intrinsic this replaces is a software loop: 4-5 % of the edge kernels' samples,
+// profiles/r02_edge_full.csv)
 __device__ __forceinline__ int nth_set_bit(uint64_t m, int r) {
-    const uint32_t lo = (uint32_t)m;
-    const int c = __popc(lo);
-    if (r < c) return (int)__fns(lo, 0, r + 1);
-    return 32 + (int)__fns((uint32_t)(m >> 32), 0, r - c + 1);
+    uint32_t w = (uint32_t)m;
+    int pos = 0;
+    int c = __popc(w);
+    if (r >= c) {
+        r -= c;
+        w = (uint32_t)(m >> 32);
+        pos = 32;
+    }
+    c = __popc(w & 0xffffu);
+    if (r >= c) {
+        r -= c;
+        w >>= 16;
+        pos += 16;
+    }
+    c = __popc(w & 0xffu);
+    if (r >= c) {
+        r -= c;
+        w >>= 8;
+        pos += 8;
+    }
+    c = __popc(w & 0xfu);
+    if (r >= c) {
+        r -= c;
+        w >>= 4;
+        pos += 4;
+    }
+    c = __popc(w & 0x3u);
+    if (r >= c) {
+        r -= c;
+        w >>= 2;
+        pos += 2;
+    }
+    return pos + (r >= (int)(w & 1u) ? 1 : 0);
 }
 
 // Edge check that evaluates a step only while nothing proves it free (n_steps <= 64).
@@ -1018,3 +1074,12 @@ extern "C" int mmmp_collide_segments(const mmmp_world* w, int robot, const void*
     return launch_edges(w, robot, (const float*)qa, (const float*)qb, ld, nullptr, E, n_steps, step, flags, out,
                         stream);
 }
+
+#ifdef MMMP_EDGE_DIAG
+extern "C" int mmmp_edge_diag(unsigned long long* out64_h) {
+    if (out64_h) MMMP_CUDA_TRY(cudaMemcpyFromSymbol(out64_h, g_diag, sizeof(unsigned long long) * 64));
+    unsigned long long zero[64] = {0};
+    MMMP_CUDA_TRY(cudaMemcpyToSymbol(g_diag, zero, sizeof(zero)));
+    return MMMP_OK;
+}
+#endif

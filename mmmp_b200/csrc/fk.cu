@@ -15,10 +15,20 @@ struct ChainSmem {
     float origin[MMMP_MAX_JOINTS + 1][12];
 };
 
-__global__ void __launch_bounds__(256)
+// Positions leave through shared memory: a thread owns one configuration, i.e. 3 (n + 1) output
+// floats at a stride of 3 (n + 1) floats -- written directly that is 32 scattered 4-byte stores per
+// instruction (round 1: 1.07 TB/s, profiles/r02_fk_full.csv: lg_throttle / mio_throttle stalls).
+// The 32 rows of a warp are contiguous in the output, so the warp parks them in a padded
+// shared-memory tile (row stride 3 (n + 1) + 1: conflict free) and copies the tile out with
+// consecutive lanes on consecutive addresses.  The configuration row comes in as two 16-byte loads.
+constexpr int FK_WARPS = 8;
+constexpr int FK_ROW_MAX = 3 * (MMMP_MAX_JOINTS + 1) + 1;
+
+__global__ void __launch_bounds__(32 * FK_WARPS)
 fk_chain_kernel(const WorldDev* __restrict__ W, int robot, const float* __restrict__ q, int ld, int64_t N,
                 float* __restrict__ out_pos, float* __restrict__ out_T) {
     __shared__ ChainSmem C;
+    __shared__ float stage[FK_WARPS][32 * FK_ROW_MAX];
     {
         const RobotDev& R = W->robots[robot];
         if (threadIdx.x == 0) C.n_joints = R.n_joints;
@@ -29,34 +39,60 @@ fk_chain_kernel(const WorldDev* __restrict__ W, int robot, const float* __restri
     __syncthreads();
     const int n = C.n_joints;
     const int L = n + 1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        Affine T;
-        affine_load(T, C.base);
-        const float* qi = q + i * ld;
-        for (int j = 0; j < n; ++j) {
-            float s, c;
-            sincosf(qi[j], &s, &c);
-            affine_step(T, C.origin[j], s, c);
-            float* p = out_pos + (i * L + j) * 3;
-            p[0] = T.m[3];
-            p[1] = T.m[7];
-            p[2] = T.m[11];
+    const int row = 3 * L, srow = row + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = stage[warp];
+    const bool vec = (ld & 3) == 0 && ((uintptr_t)q & 15) == 0;
+    for (int64_t base = ((int64_t)blockIdx.x * FK_WARPS + warp) * 32; base < N; base += (int64_t)gridDim.x * FK_WARPS * 32) {
+        const int64_t i = base + lane;
+        if (i < N) {
+            Affine T;
+            affine_load(T, C.base);
+            const float* qi = q + i * ld;
+            float qv[MMMP_MAX_JOINTS];
+            if (vec) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(qi));
+                const float4 b = ld >= 8 ? __ldg(reinterpret_cast<const float4*>(qi) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                qv[0] = a.x, qv[1] = a.y, qv[2] = a.z, qv[3] = a.w, qv[4] = b.x, qv[5] = b.y, qv[6] = b.z, qv[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < MMMP_MAX_JOINTS; ++j) qv[j] = j < n ? __ldg(qi + j) : 0.f;
+            }
+            float* mine = tile + lane * srow;
+#pragma unroll
+            for (int j = 0; j < MMMP_MAX_JOINTS; ++j) {
+                if (j < n) {
+                    float s, c;
+                    sincosf(qv[j], &s, &c);
+                    affine_step(T, C.origin[j], s, c);
+                    mine[3 * j + 0] = T.m[3];
+                    mine[3 * j + 1] = T.m[7];
+                    mine[3 * j + 2] = T.m[11];
+                    if (out_T) {
+                        float* t = out_T + (i * L + j) * 12;
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) t[k] = T.m[k];
+                    }
+                }
+            }
+            affine_mul(T, C.origin[n]);
+            mine[3 * n + 0] = T.m[3];
+            mine[3 * n + 1] = T.m[7];
+            mine[3 * n + 2] = T.m[11];
             if (out_T) {
-                float* t = out_T + (i * L + j) * 12;
+                float* t = out_T + (i * L + n) * 12;
 #pragma unroll
                 for (int k = 0; k < 12; ++k) t[k] = T.m[k];
             }
         }
-        affine_mul(T, C.origin[n]);
-        float* p = out_pos + (i * L + n) * 3;
-        p[0] = T.m[3];
-        p[1] = T.m[7];
-        p[2] = T.m[11];
-        if (out_T) {
-            float* t = out_T + (i * L + n) * 12;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) t[k] = T.m[k];
+        __syncwarp();
+        const int rows = (int)((N - base) < 32 ? (N - base) : 32);
+        float* dst = out_pos + base * row;
+        for (int e = lane; e < rows * row; e += 32) {
+            const int r = e / row;
+            dst[e] = tile[r * srow + (e - r * row)];
         }
+        __syncwarp();
     }
 }
 

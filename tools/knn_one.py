@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One neighbour scan for profiling: python tools/knn_one.py n fk|l2 Q [k]"""
+"""One neighbour scan for profiling: python tools/knn_one.py n fk|fkc|l2 Q [k]   (fkc: centroid filter rows)"""
 import os
 import sys
 
@@ -16,7 +16,7 @@ model = core.load_model("panda_spheres")
 w = core.SpatialWorld([core.RobotSpec(model, core.base_matrix((0.665, 0, 0.01), (0, 0, 1, 0)))], [core.plane()])
 lim = np.array(model["joint_limits"])
 q64, q32 = core.sample_uniform(lim[:, 0], lim[:, 1], n, 7)
-F = w.fk_features(q64, q32, 0) if metric == "fk" else core.l2_features(q64, q32)
+F = (w.fk_features(q64, q32, 0, dual=metric == "fk") if metric in ("fk", "fkc") else core.l2_features(q64, q32))
 for it in range(3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
