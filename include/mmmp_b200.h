@@ -334,7 +334,11 @@ int mmmp_knn_stats(int enable, unsigned long long* out5_h);
  * are the configurations (or fp64 features); GROUP_L2_SUM: they are fp64
  * frame positions [., ld64] from mmmp_fk_chain_f64 and metric->dim selects
  * the triples.  ambiguous_d (may be NULL) [n_query] = 1 when the fp32 scan
- * could not separate rank k from rank kc (distance gap < tie_eps).          */
+ * could have dropped a row of the float64 top k: the gap between its kc-th fp32
+ * value and the float64 k-th distance is within max(tie_eps, 4 x the largest
+ * |fp32 - float64| difference measured on the row's own candidates).  Such rows
+ * are to be searched again with more candidates (core.knn_exact, RoadmapBuilder
+ * and mmmp_roadmap_*_host do).                                              */
 int mmmp_knn_refine(const double* ref64_d, const double* query64_d, int ld64,
                     const mmmp_metric* metric_h, const int32_t* cand_idx_d,
                     const float* cand_dist_d, int64_t n_query, int kc, int k,

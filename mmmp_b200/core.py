@@ -416,7 +416,23 @@ def knn_exact(ref: Features, query: Features, k: int, pad: int = 6, exclude_self
     """scan with k+pad candidates, then fp64 re-rank -> (idx, dist64, ambiguous)."""
     kc = min(k + pad, _lib.MAX_K)
     ci, cd = knn(ref, query, kc, exclude_self, causal, query_id0)
-    return knn_refine(ref.x64, query.x64, ref.m64, ci, cd, k)
+    idx, dist, amb = knn_refine(ref.x64, query.x64, ref.m64, ci, cd, k)
+    kc_wide = min(k + 16, _lib.MAX_K - 1)
+    if not causal and kc < kc_wide and bool(amb.any()):
+        # rows whose rank k the fp32 scan could not separate from its last candidate: searched again,
+        # alone, with k + 16 candidates (self comes back at distance 0 and is dropped here)
+        bad = amb.nonzero().flatten()
+        sub = query.take(bad)
+        ci2, cd2 = knn(ref, sub, kc_wide + 1, exclude_self=False)
+        if exclude_self:
+            ids = (bad + query_id0).to(torch.int32)
+            keep = ci2 != ids[:, None]
+            order = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)[:, :kc_wide]
+            ci2, cd2 = torch.gather(ci2, 1, order).contiguous(), torch.gather(cd2, 1, order).contiguous()
+        else:
+            ci2, cd2 = ci2[:, :kc_wide].contiguous(), cd2[:, :kc_wide].contiguous()
+        idx[bad], dist[bad], amb[bad] = knn_refine(ref.x64, sub.x64, ref.m64, ci2, cd2, k)
+    return idx, dist, amb
 
 
 def radius_search(ref: Features, query: Features, r: float, strict: bool = False, exclude_self: bool = True,

@@ -57,6 +57,7 @@ __device__ float g_diag_spt = 50.f;
 struct SpatialSmem {
     int n_r;
     int n_obs;
+    int n_planes;                      // obstacles [0, n_planes) are planes
     int slots;                         // frame slots per thread (stored frames of all robots)
     int links;                         // link slots per thread (stored bounding-sphere centres)
     int mode;                          // RobotDev::frame_store / link_store row in use
@@ -124,6 +125,7 @@ __device__ __forceinline__ void stage_world(const SpatialArgs& A, unsigned char*
     if (threadIdx.x == 0) {
         hdr->n_r = A.n_r;
         hdr->n_obs = n_obs;
+        hdr->n_planes = A.W->n_planes;
         hdr->slots = A.slots;
         hdr->links = A.links;
         hdr->mode = A.mode;
@@ -312,6 +314,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
     const int n_r = hdr->n_r;
     const int mode = hdr->mode;
     const int n_obs = (flags & MMMP_CHECK_OBSTACLES) ? hdr->n_obs : 0;
+    const int n_planes = hdr->n_planes;
     const bool capsules = !(flags & MMMP_CHECK_NO_CAPSULES);
     float* cen = fr + (size_t)hdr->slots * 12 * stride;
     float* vel = cen + (size_t)hdr->links * 3 * stride;
@@ -386,7 +389,15 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                 }
                 for (int o = 0; o < n_obs; ++o) {
                     float g = INF;
-                    const bool bound_hit = sphere_vs_obstacle<GAP>(wb.x, wb.y, wb.z, B.w, obs[o], g);
+                    bool bound_hit;
+                    if (o < n_planes) {  // the same expressions as sphere_vs_obstacle's plane case, no dispatch
+                        const float4 P = *reinterpret_cast<const float4*>(obs[o].p);
+                        const float sd = fmaf(P.x, wb.x, fmaf(P.y, wb.y, P.z * wb.z)) - P.w;
+                        g = sd - B.w;
+                        bound_hit = sd <= B.w;
+                    } else {
+                        bound_hit = sphere_vs_obstacle<GAP>(wb.x, wb.y, wb.z, B.w, obs[o], g);
+                    }
                     if (GAP ? g > want : !bound_hit) {
                         if (GAP) gmin = fminf(gmin, g);
                         continue;
@@ -949,6 +960,7 @@ extern "C" int mmmp_planar_collide_edges(const mmmp_world* w, int arm, const dou
 extern "C" int mmmp_collide_configs(const mmmp_world* w, int robot, const void* q, int ld, int64_t N,
                                     uint32_t flags, uint8_t* out, void* stream) {
     if (!w || !q || !out || N < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (N == 0) return MMMP_OK;
     if (w->kind == MMMP_WORLD_PLANAR)
         return mmmp_planar_collide_configs(w, robot, (const double*)q, ld, N, flags, out, stream);
@@ -968,6 +980,7 @@ extern "C" int mmmp_collide_configs(const mmmp_world* w, int robot, const void* 
 extern "C" int mmmp_collide_robot_pairs(const mmmp_world* w, int ra, int rb, const void* qa, const void* qb,
                                         int ld, int64_t N, uint8_t* out, void* stream) {
     if (!w || !qa || !qb || !out || N < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (N == 0) return MMMP_OK;
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     const WorldDev* H = w->spatial_h;
@@ -1056,6 +1069,7 @@ extern "C" int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q,
                                   int64_t E, int n_steps, double step, uint32_t flags, uint8_t* out,
                                   void* stream) {
     if (!w || !q || !edges || !out || E < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (E == 0) return MMMP_OK;
     if (w->kind == MMMP_WORLD_PLANAR)
         return mmmp_planar_collide_edges(w, robot, (const double*)q, nullptr, ld, edges, E, n_steps, step, flags,
@@ -1067,6 +1081,7 @@ extern "C" int mmmp_collide_segments(const mmmp_world* w, int robot, const void*
                                      int64_t E, int n_steps, double step, uint32_t flags, uint8_t* out,
                                      void* stream) {
     if (!w || !qa || !qb || !out || E < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (E == 0) return MMMP_OK;
     if (w->kind == MMMP_WORLD_PLANAR)
         return mmmp_planar_collide_edges(w, robot, (const double*)qa, (const double*)qb, ld, nullptr, E, n_steps,

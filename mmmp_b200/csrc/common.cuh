@@ -74,14 +74,16 @@ struct RobotDev64 {  // fp64 chain for the re-ranking FK
     double origin[MMMP_MAX_JOINTS + 1][12];
 };
 
-struct ObstacleDev {
+struct ObstacleDev {   // p first and the struct 16-byte sized: a plane's (n, d) is one 16-byte shared-memory load
+    float p[16];
     int type;
     int body;
-    float p[16];
+    int pad[2];
 };
 
 struct WorldDev {
     int n_robots, n_obstacles, dof, n_table_words;
+    int n_planes, pad_w[3];   // obstacles are stored planes first: [0, n_planes) take the plane fast path
     RobotDev robots[MMMP_MAX_ROBOTS];
     ObstacleDev obstacles[MMMP_MAX_OBSTACLES];
     RobotDev64 robots64[MMMP_MAX_ROBOTS];
@@ -111,6 +113,15 @@ struct mmmp_world {
     PlanarDev* planar_d;
     PlanarDev* planar_h;
 };
+
+// a world's tables live on the device that was current when it was created; kernels launched on
+// another device would fault on them
+#define MMMP_CHECK_DEVICE(w)                                                        \
+    do {                                                                           \
+        int _cur = -1;                                                             \
+        MMMP_CUDA_TRY(cudaGetDevice(&_cur));                                       \
+        if ((w) && _cur != (w)->device) return MMMP_ERR_ARG;                       \
+    } while (0)
 
 #define MMMP_PLANAR_MAX_LINKS 32
 

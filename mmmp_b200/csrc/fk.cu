@@ -218,6 +218,7 @@ int fk_grid(int64_t N, int block) {
 extern "C" int mmmp_fk_chain(const mmmp_world* w, int robot, const float* q, int ld, int64_t N, float* out_pos,
                              float* out_T, void* stream) {
     if (!w || !q || !out_pos || N < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
     if (N == 0) return MMMP_OK;
@@ -229,6 +230,7 @@ extern "C" int mmmp_fk_chain(const mmmp_world* w, int robot, const float* q, int
 extern "C" int mmmp_fk_chain_f64(const mmmp_world* w, int robot, const double* q, int ld, int64_t N,
                                  double* out_pos, void* stream) {
     if (!w || !q || !out_pos || N < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
     if (N == 0) return MMMP_OK;
@@ -241,6 +243,7 @@ extern "C" int mmmp_fk_features(const mmmp_world* w, int robot, const float* q, 
                                 const int32_t* frames, const float* weights, int n_frames, float* out, int ldf,
                                 float* out_filter, int ldfilt, void* stream) {
     if (!w || !q || !out || !frames || N < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (robot < 0 || robot >= w->spatial_h->n_robots || ld < w->spatial_h->robots[robot].n_joints) return MMMP_ERR_ARG;
     if (n_frames < 1 || n_frames > MMMP_MAX_GROUPS || ldf < 3 * n_frames) return MMMP_ERR_ARG;

@@ -180,6 +180,7 @@ extern "C" int mmmp_ik_dls(const mmmp_world* w, int robot, const double* target_
                            double lambda, double tol_pos, double tol_rot, double max_step, double* q_out, int ld,
                            uint8_t* converged, float* residual, void* stream) {
     if (!w || !target_pos || !q0 || !q_out || !lo_h || !hi_h || N < 0 || max_iters < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
     if (robot < 0 || robot >= w->spatial_h->n_robots) return MMMP_ERR_ARG;
     const int n = w->spatial_h->robots[robot].n_joints;

@@ -71,10 +71,12 @@ knn_refine_kernel(const double* __restrict__ ref, const double* __restrict__ que
         int di[MMMP_MAX_K];
         int n = 0;
         const double* a = query + q * ld;
+        double err32 = 0.0;   // largest |fp32 scan value - float64 value| seen on this row's candidates
         for (int c = 0; c < kc; ++c) {
             const int id = cand_idx[(size_t)q * kc + c];
             if (id < 0) continue;
             const double d = exact_metric_f64(kind, dim, group, a, ref + (int64_t)id * ld);
+            err32 = fmax(err32, fabs(d - (double)cand_dist[(size_t)q * kc + c]));
             int p = n++;
             while (p > 0 && (dv[p - 1] > d || (dv[p - 1] == d && di[p - 1] > id))) {
                 dv[p] = dv[p - 1];
@@ -104,13 +106,15 @@ knn_refine_kernel(const double* __restrict__ ref, const double* __restrict__ que
             if (out_dist) out_dist[(size_t)q * k + c] = c < n ? dv[c] : CUDART_INF;
         }
         if (ambiguous) {
-            // the fp32 scan could have dropped a row that belongs in the top k if its own
-            // kc-th value is not clearly beyond the k-th
+            // The fp32 scan kept the kc smallest fp32 values.  A row it dropped has an fp32 value of
+            // at least vl (its kc-th); that row belongs in the float64 top k only if fp32 error can
+            // bridge the gap between vl and the float64 k-th distance.  The error is not assumed: it
+            // is measured on this row's own candidates (err32) and given a factor 4 in hand, with
+            // tie_eps as the floor (an absolute 1e-6 ignored the metric's magnitude).
             uint8_t amb = 0;
             if (kc > k && n >= kc) {
-                const float vk = cand_dist[(size_t)q * kc + (k - 1)];
-                const float vl = cand_dist[(size_t)q * kc + (kc - 1)];
-                if ((double)vl - (double)vk <= tie_eps) amb = 1;
+                const double vl = (double)cand_dist[(size_t)q * kc + (kc - 1)];
+                if (vl - dv[k - 1] <= fmax(tie_eps, 4.0 * err32)) amb = 1;
             }
             ambiguous[q] = amb;
         }

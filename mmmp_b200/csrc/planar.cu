@@ -251,6 +251,7 @@ int planar_grid(int64_t items, int per_cta) {
 extern "C" int mmmp_planar_fk(const mmmp_world* w, int arm, const double* q, int ld, int64_t N, double* out,
                               void* stream) {
     if (!w || !q || !out || N < 0) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (w->kind != MMMP_WORLD_PLANAR) return MMMP_ERR_KIND;
     if (arm < 0 || arm >= w->planar_h->n_arms) return MMMP_ERR_ARG;
     if (N == 0) return MMMP_OK;
@@ -262,6 +263,7 @@ extern "C" int mmmp_planar_fk(const mmmp_world* w, int arm, const double* q, int
 extern "C" int mmmp_planar_collide_configs(const mmmp_world* w, int arm, const double* q, int ld, int64_t N,
                                            uint32_t flags, uint8_t* out, void* stream) {
     if (arm >= w->planar_h->n_arms) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     MMMP_LAUNCH(planar_configs_kernel, planar_grid(N, 128), 128, 0, stream, w->planar_d, arm, q, ld, N, flags, out);
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
@@ -271,6 +273,7 @@ extern "C" int mmmp_planar_collide_edges(const mmmp_world* w, int arm, const dou
                                          const int32_t* edges, int64_t E, int n_steps, double step, uint32_t flags,
                                          uint8_t* out, void* stream) {
     if (arm >= w->planar_h->n_arms) return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
     if (n_steps < 1 || n_steps > 4096) return MMMP_ERR_ARG;
     MMMP_LAUNCH(planar_edges_kernel, planar_grid(E, 4), 128, 0, stream, w->planar_d, arm, qa, qb, ld, edges, E,
                 n_steps, step, flags, out);

@@ -333,16 +333,25 @@ extern "C" int mmmp_world_create(const mmmp_robot_desc* robots, int n_robots,
     }
     H->dof = dof;
     H->n_table_words = table_words;
-    for (int o = 0; o < n_obstacles; ++o) {
-        ObstacleDev& O = H->obstacles[o];
-        O.type = obstacles[o].type;
-        O.body = obstacles[o].body;
-        if (O.type < MMMP_OBS_PLANE || O.type > MMMP_OBS_CYLINDER) {
-            free(H);
-            return MMMP_ERR_KIND;
+    // planes first (a verdict is an OR over the obstacles: their order is free), so that the kernels
+    // can test them without the type dispatch
+    int slot = 0;
+    H->n_planes = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int o = 0; o < n_obstacles; ++o) {
+            const int type = obstacles[o].type;
+            if (type < MMMP_OBS_PLANE || type > MMMP_OBS_CYLINDER) {
+                free(H);
+                return MMMP_ERR_KIND;
+            }
+            if ((type == MMMP_OBS_PLANE) != (pass == 0)) continue;
+            ObstacleDev& O = H->obstacles[slot++];
+            O.type = type;
+            O.body = obstacles[o].body;
+            O.pad[0] = O.pad[1] = 0;
+            for (int i = 0; i < 16; ++i) O.p[i] = (float)obstacles[o].p[i];
+            if (pass == 0) H->n_planes++;
         }
-        for (int i = 0; i < 16; ++i) O.p[i] = (float)obstacles[o].p[i];
-    }
     mmmp_world* w = new (std::nothrow) mmmp_world();
     if (!w) {
         free(H);
