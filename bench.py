@@ -467,6 +467,7 @@ def run_ours(args):
             flop_edge = (counters["evals_adaptive"] * e.get("fp32_flop_per_eval_adaptive", 0.0) +
                          counters["evals_hard"] * e.get("fp32_flop_per_eval_hard", 0.0)) * share
             edge_roof = roof("collide_edges_adaptive_kernel<4> + collide_edges_hard_kernel", edge_ms, flop_edge, {
+                "registers": [e.get("adaptive", {}).get("registers"), e.get("hard", {}).get("registers")],
                 "traffic": e.get("dram_bytes_per_launch_pair"),
                 "unit_of_work": "configuration evaluated (FK of 7 joints + plane / self-pair bounding tests + clearance)",
                 "evaluations_per_edge": counters["evals_per_edge"], "steps_per_edge": 50,
@@ -480,7 +481,8 @@ def run_ours(args):
             k_ = kf.get("knn_scan", {})
             flop_scan = counters["tile_visits"] * k_.get("fp32_flop_per_tile_visit", 0.0) * share
             traffic = k_.get("dram_bytes_per_launch")
-            scan_roof = roof("knn_scan_kernel<1,1>", scan_ms, flop_scan, {
+            scan_roof = roof(k_.get("kernel", "knn_scan_kernel").replace("void ", ""), scan_ms, flop_scan, {
+                "registers": k_.get("registers"),
                 "traffic": traffic,
                 "unit_of_work": "tile visit (128 queries x 128 reference rows through the centroid filter + the exact "
                                 "evaluations and insertions it triggers)",

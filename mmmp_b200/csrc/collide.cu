@@ -29,6 +29,10 @@
 namespace {
 
 #define MMMP_GAP_SLACK 1.0e-4f   // metres: clearance kept in hand when a step is skipped
+#ifndef MMMP_COLLIDE_MINB
+#define MMMP_COLLIDE_MINB 5       // resident CTAs per SM the register budget must allow (96 registers; the
+                                  // 216 B-per-thread column lets 5 fit in shared memory as well)
+#endif
 #ifndef MMMP_EDGE_LANES
 #define MMMP_EDGE_LANES 4          // lanes per edge in the step-skipping pass (4: 8 edges per warp)
 #endif
@@ -79,12 +83,16 @@ struct SpatialArgs {
 };
 
 // per-thread shared-memory column, element e of this thread at fr[e * stride]:
-//   [0, 12*slots)                 frame poses (row-major 3x4) of the frames read back later
-//   [12*slots, +3*links)          world centres of the link bounding spheres read back later
-//   [12*slots + 3*links, +slots)  mode 1: travel bound of each stored frame per unit t
-// (RobotDev::frame_store / link_store map frames and links to slots; a Panda checked for self
-// and obstacle collision keeps 6 frames and 6 centres: 360 B per thread, 4 CTAs per SM)
-#define MMMP_COLUMN_FLOATS(slots, links, mode) ((12 + ((mode) ? 1 : 0)) * (slots) + 3 * (links))
+//   [0, 9*links)            per stored link: world centre of its bounding sphere (3), world end points of
+//                           its bounding capsule (3 + 3)
+//   [9*links, +slots)       mode 1: travel bound of each stored frame per unit t
+// (RobotDev::link_store / frame_store map links and frames to slots.)  Round 1 parked the 3x4 POSES
+// of the frames instead (360 B per thread for a Panda: 53 KB per CTA, 4 CTAs per SM).  Poses are only
+// needed when a link pair survives both its bounding spheres and its capsules -- 2 % of the free
+// configurations -- and are then recomputed by a second sweep over the joints (frames_of); what is
+// read back for every pair is 9 floats per link: 216 B per thread, 37 KB per CTA, so 5 CTAs fit
+// beside 96 registers per thread.
+#define MMMP_COLUMN_FLOATS(slots, links, mode) (9 * (links) + ((mode) ? (slots) : 0))
 
 // --- q loaders -------------------------------------------------------------
 struct QConfig {
@@ -154,19 +162,32 @@ __device__ __forceinline__ void stage_world(const SpatialArgs& A, unsigned char*
     __syncthreads();
 }
 
-// frame f (1..n) of a robot from the thread's shared-memory column; f == 0 is the
-// identity because frame-0 (base link) spheres are stored in world coordinates
-__device__ __forceinline__ void load_frame(Affine& T, const float* fr, int stride, int slot0, int fslot) {
-    if (fslot < 0) {  // frame 0 (never stored)
+// Poses of frames fa and fb of robot lr (frame f = after joint f - 1; frame 0 is the identity because
+// base-link spheres are stored in world coordinates), recomputed with the SAME operations as the
+// sweep of spatial_eval, hence bit-identical to what that sweep held.
+template <class QL>
+__device__ __noinline__ void frames_of(const RobotDev& R, const QL& ql, int lr, int col, int fa, int fb, Affine& TA,
+                                       Affine& TB) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) T.m[i] = (i == 0 || i == 5 || i == 10) ? 1.f : 0.f;
-        return;
+    for (int i = 0; i < 12; ++i) TA.m[i] = TB.m[i] = (i == 0 || i == 5 || i == 10) ? 1.f : 0.f;
+    Affine T;
+    affine_load(T, R.base);
+    const int last = fa > fb ? fa : fb;
+#pragma unroll 1
+    for (int j = 0; j < last; ++j) {
+        const float qj = ql.get(lr, col + j);
+        float s, c;
+#ifdef MMMP_COLLIDE_ACCURATE_SINCOS
+        sincosf(qj, &s, &c);
+#else
+        __sincosf(qj, &s, &c);
+#endif
+        if (R.origin_rx[j]) affine_step_rx(T, R.origin[j], s, c);
+        else affine_step(T, R.origin[j], s, c);
+        if (j + 1 == fa) TA = T;
+        if (j + 1 == fb) TB = T;
     }
-    const float* p = fr + (size_t)(slot0 + fslot) * 12 * stride;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) T.m[i] = p[i * stride];
 }
-
 
 // spheres of link lb (robot RB, pose TB) against spheres of link la (robot RA, pose TA); the
 // caller has already found the two bounding spheres overlapping (GAP: closer than `want`).
@@ -221,16 +242,12 @@ __device__ __forceinline__ bool link_pair_hit(const RobotDev& RA, int la, const 
     return false;
 }
 
-// Squared distance between the axes of the bounding capsules of link la (pose TA) and link lb (pose
-// TB), and the sum of their radii.  The closest pair of points is found in fp32 (Ericson's segment /
-// segment clamp sequence); whatever rounding does to the parameters, the value is a distance between
-// two points that DO lie on the segments, so it can exceed the true minimum only by the (second
-// order) effect of the parameter error -- callers keep a 0.1 mm margin.
-__device__ __forceinline__ void capsule_pair(const RobotDev& RA, int la, const Affine& TA, const RobotDev& RB, int lb,
-                                             const Affine& TB, float& d2, float& rr) {
-    const float4 a0 = RA.cap_a[la], a1 = RA.cap_b[la], b0 = RB.cap_a[lb], b1 = RB.cap_b[lb];
-    const float3 p1 = affine_point(TA, a0.x, a0.y, a0.z), q1 = affine_point(TA, a1.x, a1.y, a1.z);
-    const float3 p2 = affine_point(TB, b0.x, b0.y, b0.z), q2 = affine_point(TB, b1.x, b1.y, b1.z);
+// Squared distance between two segments p1-q1 and p2-q2 (the world-space axes of two bounding
+// capsules).  The closest pair of points is found in fp32 (Ericson's segment / segment clamp
+// sequence); whatever rounding does to the parameters, the value is a distance between two points
+// that DO lie on the segments, so it can exceed the true minimum only by the (second order) effect
+// of the parameter error -- callers keep a 0.1 mm margin.
+__device__ __forceinline__ float segment_d2(float3 p1, float3 q1, float3 p2, float3 q2) {
     const float d1x = q1.x - p1.x, d1y = q1.y - p1.y, d1z = q1.z - p1.z;
     const float d2x = q2.x - p2.x, d2y = q2.y - p2.y, d2z = q2.z - p2.z;
     const float rx = p1.x - p2.x, ry = p1.y - p2.y, rz = p1.z - p2.z;
@@ -244,21 +261,32 @@ __device__ __forceinline__ void capsule_pair(const RobotDev& RA, int la, const A
     sp = __saturatef(fmaf(b, tp, -c) * inv_a);              // ... and of segment 1 to Q(tp): covers Ericson's
                                                             // clamp cases and degenerate (point) segments
     const float ex = fmaf(sp, d1x, rx) - tp * d2x, ey = fmaf(sp, d1y, ry) - tp * d2y, ez = fmaf(sp, d1z, rz) - tp * d2z;
-    d2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-    rr = a0.w + b0.w;
+    return fmaf(ex, ex, fmaf(ey, ey, ez * ez));
 }
 
 #define MMMP_CAPSULE_MARGIN 1.0e-4f   // metres kept in hand when a capsule test skips a descent
 
+// world end points of link slot ls's capsule from a thread's column (see MMMP_COLUMN_FLOATS)
+__device__ __forceinline__ void load_capsule(const float* cl, int stride, int ls, float3& a, float3& b) {
+    const float* p = cl + (size_t)(9 * ls + 3) * stride;
+    a = make_float3(p[0], p[stride], p[2 * stride]);
+    b = make_float3(p[3 * stride], p[4 * stride], p[5 * stride]);
+}
+
 // Link pair whose bounding spheres overlap (GAP: are closer than `want`): capsule against capsule
-// first; only if that cannot separate them either (GAP: cannot prove `want`) are the spheres of the
-// two links tested.  Returns true on a collision; GAP: g = clearance proven for the pair.
-template <bool GAP>
-__device__ __forceinline__ bool link_pair_refine(const RobotDev& RA, int la, const Affine& TA, const RobotDev& RB, int lb,
-                                                 const Affine& TB, bool capsules, float want, float& g) {
+// first (world end points parked by the sweep); only if that cannot separate them either (GAP:
+// cannot prove `want`) are the two frame poses recomputed and the spheres of the two links tested.
+// Returns true on a collision; GAP: g = clearance proven for the pair.
+template <class QL, bool GAP>
+__device__ __forceinline__ bool link_pair_refine(const RobotDev& RA, int la, int lra, int cola, const float* cla, int lsa,
+                                                 const RobotDev& RB, int lb, int lrb, int colb, const float* clb, int lsb,
+                                                 const QL& ql, int stride, bool capsules, float want, float& g) {
     if (capsules && RA.cap_a[la].w >= 0.f && RB.cap_a[lb].w >= 0.f) {
-        float d2, rr;
-        capsule_pair(RA, la, TA, RB, lb, TB, d2, rr);
+        float3 p1, q1, p2, q2;
+        load_capsule(cla, stride, lsa, p1, q1);
+        load_capsule(clb, stride, lsb, p2, q2);
+        const float d2 = segment_d2(p1, q1, p2, q2);
+        const float rr = RA.cap_a[la].w + RB.cap_a[lb].w;
         if (GAP) {
             const float gc = fast_sqrt(d2) - rr - MMMP_CAPSULE_MARGIN;
             if (gc > want) {
@@ -269,6 +297,14 @@ __device__ __forceinline__ bool link_pair_refine(const RobotDev& RA, int la, con
             const float lim = rr + MMMP_CAPSULE_MARGIN;
             if (d2 > lim * lim) return false;
         }
+    }
+    Affine TA, TB, unused;
+    const int fa = RA.link_frame[la], fb = RB.link_frame[lb];
+    if (&RA == &RB) {
+        frames_of(RA, ql, lra, cola, fa, fb, TA, TB);
+    } else {
+        frames_of(RA, ql, lra, cola, fa, 0, TA, unused);
+        frames_of(RB, ql, lrb, colb, fb, 0, TB, unused);
     }
     g = __int_as_float(0x7f800000);
     return link_pair_hit<GAP>(RA, la, TA, RB, lb, TB, want, g);
@@ -316,8 +352,7 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
     const int n_obs = (flags & MMMP_CHECK_OBSTACLES) ? hdr->n_obs : 0;
     const int n_planes = hdr->n_planes;
     const bool capsules = !(flags & MMMP_CHECK_NO_CAPSULES);
-    float* cen = fr + (size_t)hdr->slots * 12 * stride;
-    float* vel = cen + (size_t)hdr->links * 3 * stride;
+    float* vel = fr + (size_t)hdr->links * 9 * stride;
     float tsafe = INF;
 #ifdef MMMP_EDGE_DIAG
     int why = 30;
@@ -329,14 +364,15 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
         Affine T;
         affine_load(T, R.base);
         const int slot0 = hdr->frame_slot[lr];
-        float* cl = cen + (size_t)hdr->link_slot[lr] * 3 * stride;
+        float* cl = fr + (size_t)hdr->link_slot[lr] * 9 * stride;
         for (int l = R.frame_link_begin[0]; l < R.frame_link_begin[1]; ++l) {  // base links: world coordinates
             const int ls = R.link_store[mode][l];
             if (ls < 0) continue;
-            const float4 B = R.link_bound[l];
-            cl[(3 * ls + 0) * stride] = B.x;
-            cl[(3 * ls + 1) * stride] = B.y;
-            cl[(3 * ls + 2) * stride] = B.z;
+            const float4 B = R.link_bound[l], ca = R.cap_a[l], cb = R.cap_b[l];
+            float* p = cl + (size_t)9 * ls * stride;
+            p[0] = B.x, p[stride] = B.y, p[2 * stride] = B.z;
+            p[3 * stride] = ca.x, p[4 * stride] = ca.y, p[5 * stride] = ca.z;
+            p[6 * stride] = cb.x, p[7 * stride] = cb.y, p[8 * stride] = cb.z;
         }
         bool hit = false;
         float adq[MMMP_MAX_JOINTS];
@@ -357,11 +393,6 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
             if (R.origin_rx[j]) affine_step_rx(T, R.origin[j], s, c);
             else affine_step(T, R.origin[j], s, c);
             const int fs = R.frame_store[mode][j + 1];
-            if (fs >= 0) {
-                float* p = fr + (size_t)(slot0 + fs) * 12 * stride;
-#pragma unroll
-                for (int i = 0; i < 12; ++i) p[i * stride] = T.m[i];
-            }
             float inv_v = 0.f, want = 0.f;
             if (GAP) {
                 const float dj = fabsf(ql.delta(lr, col + j));
@@ -382,10 +413,13 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                 if (B.w < 0.f) continue;
                 const float3 wb = affine_point(T, B.x, B.y, B.z);
                 const int ls = R.link_store[mode][l];
-                if (ls >= 0) {
-                    cl[(3 * ls + 0) * stride] = wb.x;
-                    cl[(3 * ls + 1) * stride] = wb.y;
-                    cl[(3 * ls + 2) * stride] = wb.z;
+                if (ls >= 0) {  // what the link-pair tests read back: centre and capsule end points, world space
+                    const float4 ca = R.cap_a[l], cb = R.cap_b[l];
+                    const float3 wa = affine_point(T, ca.x, ca.y, ca.z), wc = affine_point(T, cb.x, cb.y, cb.z);
+                    float* p = cl + (size_t)9 * ls * stride;
+                    p[0] = wb.x, p[stride] = wb.y, p[2 * stride] = wb.z;
+                    p[3 * stride] = wa.x, p[4 * stride] = wa.y, p[5 * stride] = wa.z;
+                    p[6 * stride] = wc.x, p[7 * stride] = wc.y, p[8 * stride] = wc.z;
                 }
                 for (int o = 0; o < n_obs; ++o) {
                     float g = INF;
@@ -419,9 +453,9 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                 const int fa = R.link_frame[pr.x], fb = R.link_frame[pr.y];
                 const float ra = R.link_bound[pr.x].w, rb = R.link_bound[pr.y].w;
                 const int sa = R.link_store[mode][pr.x], sb = R.link_store[mode][pr.y];
-                const float dx = cl[(3 * sa + 0) * stride] - cl[(3 * sb + 0) * stride];
-                const float dy = cl[(3 * sa + 1) * stride] - cl[(3 * sb + 1) * stride];
-                const float dz = cl[(3 * sa + 2) * stride] - cl[(3 * sb + 2) * stride];
+                const float dx = cl[(9 * sa + 0) * stride] - cl[(9 * sb + 0) * stride];
+                const float dy = cl[(9 * sa + 1) * stride] - cl[(9 * sb + 1) * stride];
+                const float dz = cl[(9 * sa + 2) * stride] - cl[(9 * sb + 2) * stride];
                 const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 const float rr = ra + rb;
                 float g = INF, v = 0.f, want = 0.f;
@@ -434,10 +468,9 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                     g = fast_sqrt(d2) - rr;
                 }
                 if (GAP ? g <= want : d2 <= rr * rr) {
-                    Affine TA, TB;
-                    load_frame(TA, fr, stride, slot0, R.frame_store[mode][fa]);
-                    load_frame(TB, fr, stride, slot0, R.frame_store[mode][fb]);
-                    if (link_pair_refine<GAP>(R, pr.x, TA, R, pr.y, TB, capsules, want, g)) return HIT;
+                    if (link_pair_refine<QL, GAP>(R, pr.x, lr, col, cl, sa, R, pr.y, lr, col, cl, sb, ql, stride, capsules,
+                                                  want, g))
+                        return HIT;
                 }
                 if (GAP) MMMP_DIAG_MIN(__fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)), 16 + pi);
             }
@@ -446,25 +479,25 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
     if ((flags & MMMP_CHECK_ROBOTS) && n_r > 1) {
         for (int l1 = 0; l1 < n_r; ++l1) {
             const RobotDev& R1 = robs[l1];
-            const float* c1 = cen + (size_t)hdr->link_slot[l1] * 3 * stride;
+            const float* c1 = fr + (size_t)hdr->link_slot[l1] * 9 * stride;
             for (int l2 = l1 + 1; l2 < n_r; ++l2) {
                 const RobotDev& R2 = robs[l2];
-                const float* c2 = cen + (size_t)hdr->link_slot[l2] * 3 * stride;
+                const float* c2 = fr + (size_t)hdr->link_slot[l2] * 9 * stride;
                 for (int la = 0; la < R1.n_links; ++la) {
                     const float ra = R1.link_bound[la].w;
                     if (ra < 0.f) continue;
                     const int fa = R1.link_frame[la];
                     const int sa = R1.link_store[mode][la];
-                    const float ax = c1[(3 * sa + 0) * stride], ay = c1[(3 * sa + 1) * stride],
-                                az = c1[(3 * sa + 2) * stride];
+                    const float ax = c1[(9 * sa + 0) * stride], ay = c1[(9 * sa + 1) * stride],
+                                az = c1[(9 * sa + 2) * stride];
                     for (int lb = 0; lb < R2.n_links; ++lb) {
                         const float rb = R2.link_bound[lb].w;
                         if (rb < 0.f) continue;
                         const int fb = R2.link_frame[lb];
                         if (fa == 0 && fb == 0) continue;  // static pair
                         const int sb = R2.link_store[mode][lb];
-                        const float dx = ax - c2[(3 * sb + 0) * stride], dy = ay - c2[(3 * sb + 1) * stride],
-                                    dz = az - c2[(3 * sb + 2) * stride];
+                        const float dx = ax - c2[(9 * sb + 0) * stride], dy = ay - c2[(9 * sb + 1) * stride],
+                                    dz = az - c2[(9 * sb + 2) * stride];
                         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                         const float rr = ra + rb;
                         float g = INF, v = 0.f, want = 0.f;
@@ -476,10 +509,9 @@ __device__ float spatial_eval(const WorldDev* __restrict__ Wg, const SpatialSmem
                             g = fast_sqrt(d2) - rr;
                         }
                         if (GAP ? g <= want : d2 <= rr * rr) {
-                            Affine TA, TB;
-                            load_frame(TA, fr, stride, hdr->frame_slot[l1], R1.frame_store[mode][fa]);
-                            load_frame(TB, fr, stride, hdr->frame_slot[l2], R2.frame_store[mode][fb]);
-                            if (link_pair_refine<GAP>(R1, la, TA, R2, lb, TB, capsules, want, g)) return HIT;
+                            if (link_pair_refine<QL, GAP>(R1, la, l1, hdr->col[l1], c1, sa, R2, lb, l2, hdr->col[l2], c2, sb, ql,
+                                                          stride, capsules, want, g))
+                                return HIT;
                         }
                         if (GAP) MMMP_DIAG_MIN(__fdividef(g - MMMP_GAP_SLACK, fmaxf(v, 1e-20f)), 31);
                     }
@@ -507,7 +539,7 @@ __device__ __forceinline__ bool spatial_in_collision(const WorldDev* __restrict_
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MMMP_COLLIDE_MINB)
 collide_configs_kernel(SpatialArgs A, const float* __restrict__ q, int ld, int64_t N, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     SpatialSmem* hdr;
@@ -523,7 +555,7 @@ collide_configs_kernel(SpatialArgs A, const float* __restrict__ q, int ld, int64
     }
 }
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MMMP_COLLIDE_MINB)
 collide_pairs_kernel(SpatialArgs A, const float* __restrict__ qa, const float* __restrict__ qb, int ld,
                      int64_t N, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -543,7 +575,7 @@ collide_pairs_kernel(SpatialArgs A, const float* __restrict__ qa, const float* _
 // Exhaustive edge check: one warp per edge; lane l takes steps l*rounds + r in round r so that
 // every round spreads over the whole edge, warp-ballot early exit.  Verdict = OR over all
 // steps = reference semantics (decoupled_prm.py:855-863).
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MMMP_COLLIDE_MINB)
 collide_edges_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base, int ld,
                      const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
                      uint8_t* __restrict__ out) {
@@ -634,7 +666,7 @@ __device__ __forceinline__ int nth_set_bit(uint64_t m, int r) {
 // empty writes the verdict and takes the next edge of the warp's contiguous chunk, so slow
 // edges never stall the other groups.
 template <int L>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MMMP_COLLIDE_MINB)
 collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base,
                               int ld, const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
                               float want_scale, int hard_after, int64_t* __restrict__ hard_edge,
@@ -794,7 +826,7 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
 // Verdict-only evaluation; an edge found colliding drops its remaining steps.  The pair tables
 // were already looked up for every step of a deferred edge.
 #define MMMP_HARD_BATCH 8
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MMMP_COLLIDE_MINB)
 collide_edges_hard_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base, int ld,
                           const int32_t* __restrict__ edges, const int64_t* __restrict__ hard_edge,
                           const unsigned long long* __restrict__ hard_mask,
