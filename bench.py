@@ -375,6 +375,10 @@ def run_ours(args):
     launches = core.launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     phases = timer.collect()
+    all_phases = [phases]
+    if world_size > 1:          # every rank's phase table, to name the limiter of a multi-GPU step
+        all_phases = [None] * world_size
+        dist.all_gather_object(all_phases, {k_: round(v / args.steps, 3) for k_, v in phases.items()})
     clk = clocks.stop() if rank == 0 else None
     for b in builders.values():
         b.timer = None
@@ -522,6 +526,7 @@ def run_ours(args):
             "shard_parity": shard_parity,
             "configs_checked_per_s_upper": value * 50,
             "phases_ms_per_step_rank0": {k_: v / args.steps for k_, v in phases.items()},
+            "phases_ms_per_step_all_ranks": all_phases if world_size > 1 else None,
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te[0]) / args.steps,
