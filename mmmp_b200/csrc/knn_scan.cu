@@ -1045,16 +1045,11 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     MMMP_CUDA_TRY(cudaGetDevice(&dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // queries per thread: measured on B200 (1M x 1M, FK and joint-space metrics), one query per
-    // thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM
+    // queries per thread: measured on B200 in round 1 (1M x 1M, FK and joint-space metrics), one
+    // query per thread wins -- smaller CTA boxes cull more tiles and more CTAs fit an SM; the Q = 2
+    // instantiations are gone (the kernel keeps its Q parameter)
     const bool ranged = frac_lo >= 0.0;
-    const int qmax = (F4 == 1 && !ranged) ? 2 : 1;
-    int Q = 1;
-    if (const char* e = getenv("MMMP_KNN_Q")) {
-        const int q = atoi(e);
-        if ((q == 1 || q == 2) && q <= qmax) Q = q;
-    }
-    while (Q > 1 && scan_smem(F4, Q, k, S) > (size_t)max_smem) Q >>= 1;
+    const int Q = 1;
     if (scan_smem(F4, Q, k, S) > (size_t)max_smem) return MMMP_ERR_LIMIT;
     bool cull = !causal && n_ref >= KNN_CULL_MIN;
     if (const char* e = getenv("MMMP_KNN_CULL")) cull = cull && atoi(e) != 0;
@@ -1168,7 +1163,6 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     switch (dual ? 0 : F4 * 10 + Q) {
         case 0: rc = launch_scan<2, 1, true>(A, n_qblocks, stream); break;
         case 11: rc = launch_scan<1, 1>(A, n_qblocks, stream); break;
-        case 12: rc = launch_scan<1, 2>(A, n_qblocks, stream); break;
         case 21: rc = launch_scan<2, 1>(A, n_qblocks, stream); break;
         case 41: rc = launch_scan<4, 1>(A, n_qblocks, stream); break;
         case 81: rc = launch_scan<8, 1>(A, n_qblocks, stream); break;

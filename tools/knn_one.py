@@ -11,7 +11,6 @@ from mmmp_b200 import core  # noqa: E402
 
 n, metric, Q = int(sys.argv[1]), sys.argv[2], sys.argv[3]
 k = int(sys.argv[4]) if len(sys.argv) > 4 else 16
-os.environ["MMMP_KNN_Q"] = Q
 model = core.load_model("panda_spheres")
 w = core.SpatialWorld([core.RobotSpec(model, core.base_matrix((0.665, 0, 0.01), (0, 0, 1, 0)))], [core.plane()])
 lim = np.array(model["joint_limits"])
