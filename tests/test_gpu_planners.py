@@ -236,6 +236,7 @@ def test_cbs_prm_paths_are_collision_free_under_hull_oracle(cuda):
     from mmmp_b200.planners.prm.pybullet.decoupled.cbsprm import CBSPRM
     from oracle.hull import PandaHullChecker
     env = _panda_env(2)
+    np.random.seed(5)     # the 10 + 10 start / goal poses come from numpy's global stream, as in the reference
     prm = CBSPRM(env, load_roadmap=None, maxdist=0.1, k1=12, k2=8, build_type='n', prm_type='degree', n=400, t=0,
                  time_step=0.1, local_step=0.02, seed=5)
     assert prm.compute_combined_nr_nodes() == 2 * (400 + 49)
@@ -486,6 +487,7 @@ def test_prioritized_prm_paths_are_collision_free_under_hull_oracle(cuda):
     from mmmp_b200.planners.prm.pybullet.decoupled.prioritized_prm import PrioritizedPRM
     from oracle.hull import PandaHullChecker
     env = _panda_env(2)
+    np.random.seed(5)     # the 10 + 10 start / goal poses come from numpy's global stream, as in the reference
     prm = PrioritizedPRM(env, load_roadmap=None, maxdist=0.1, k1=12, k2=8, build_type='n', prm_type='degree', n=400, t=0,
                          time_step=0.1, local_step=0.02, seed=5)
     assert prm.compute_combined_nr_nodes() == 2 * (400 + 49)
