@@ -943,17 +943,25 @@ int pick_launch(K kernel, const mmmp_world* w, const SpatialArgs& A, int64_t wor
     MMMP_CUDA_TRY(cudaGetDevice(&dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    block = 128;
-    smem = smem_bytes(w, A, block);
-    while (smem > (size_t)max_smem && block > 32) {
-        block >>= 1;
-        smem = smem_bytes(w, A, block);
-    }
-    if (smem > (size_t)max_smem) return MMMP_ERR_LIMIT;
-    MMMP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // CTA size: the staged world tables are a fixed cost per CTA and the columns scale with the
+    // threads, so for wide columns (two-robot composite rows: 848 B per thread + 19 KB of tables)
+    // smaller CTAs keep more THREADS resident -- take the size with the most threads per SM
+    block = 0;
     int per_sm = 1;
-    MMMP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
-    if (per_sm < 1) per_sm = 1;
+    for (int b = 128; b >= 32; b >>= 1) {
+        const size_t need = smem_bytes(w, A, b);
+        if (need > (size_t)max_smem) continue;
+        MMMP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        int n = 0;
+        MMMP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, b, need));
+        if (n * b > per_sm * block) {
+            block = b;
+            per_sm = n;
+            smem = need;
+        }
+    }
+    if (block == 0) return MMMP_ERR_LIMIT;
+    MMMP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t want = (total_items + work_items_per_cta_hint - 1) / work_items_per_cta_hint;
     const int64_t resident = (int64_t)sms * per_sm;
     // persistent grid: a whole number of waves, never more CTAs than work
