@@ -56,8 +56,8 @@ def launch_list():
         cnt[name] += 1
     total = sum(tot.values())
     with open(os.path.join(DST, f"{R}_launch_list_summary.csv"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 600: bench.py --steps 1 --warmup 1 "
-                f"--nodes 250000 --no-cpu (first 600 launches, 1 GPU)\n"
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 1000: bench.py --steps 1 --warmup 1 "
+                f"--no-cpu --no-configs (1 M nodes per arm as in the bench line; 1 GPU; warm-up, timed step and e2e steps)\n"
                 "# per-launch times are cold-cache/serialised: compare SHARES\nkernel,launches,total_ms,share\n")
         for k in sorted(tot, key=lambda k: -tot[k]):
             f.write(f"\"{k}\",{cnt[k]},{tot[k]:.3f},{tot[k] / total:.4f}\n")
@@ -97,8 +97,9 @@ def full(rep_name, out_name):
 
 
 launch_list()
-full(f"{R}_knn_scan.ncu-rep", f"{R}_knn_scan_full.csv")
-full(f"{R}_edge.ncu-rep", f"{R}_edge_full.csv")
+if R == "r01":   # later rounds: tools/kernel_flops.py writes the per-kernel summaries
+    full(f"{R}_knn_scan.ncu-rep", f"{R}_knn_scan_full.csv")
+    full(f"{R}_edge.ncu-rep", f"{R}_edge_full.csv")
 for name in (f"{R}_bench_1gpu.json", f"{R}_bench_reference.json", f"{R}_bench_2gpu.json", f"{R}_disagreement.txt",
              f"{R}_phase_probe.txt", f"{R}_configs_probe.txt", f"{R}_bench_4gpu.json", f"{R}_bench_8gpu.json"):
     p = os.path.join(SRC, name)
