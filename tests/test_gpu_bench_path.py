@@ -214,3 +214,41 @@ def test_sharded_build_equals_single_rank_build(core, cuda):
             idx[rows.long()], dist[rows.long()] = i2, d2
         assert torch.equal(idx, ref["idx"]) and torch.equal(dist, ref["dist"])
     world.close()
+
+
+def test_kuka_roadmap_build_vs_float64_oracle(core, cuda):
+    """The KUKA iiwa14 chain (URDF joint origins, the reference's own collision spheres) through the
+    same builder: samples free of the obstacles, the FK metric over the frames of ITS chain
+    (mmmp_fk_metric_groups on general origins: no modified-DH shortcut), candidates, edge verdicts,
+    accept pass.  Neighbours against a float64 brute force on the oracle's generic chain
+    (oracle/chain.chain_frames), edges against the float64 sphere oracle.  (Self collision is off: the
+    URDF's spheres of links two apart always overlap, geometry/kuka_iiwa14_spheres.json.)"""
+    from mmmp_b200._lib import CHECK_OBSTACLES
+    from mmmp_b200.roadmap import RoadmapBuilder
+    from oracle import chain
+    from oracle.spheres import SphereChecker, model_origins
+    m = core.load_model("kuka_iiwa14_spheres")
+    base = core.base_matrix((0.1, -0.2, 0.0), (0, 0, 0.38268343, 0.92387953))
+    obstacles = [core.plane((0, 0, 1), -0.2), core.box((0.5, 0.1, 0.5), (0.1, 0.3, 0.1)), core.sphere((-0.3, 0.4, 0.8), 0.2)]
+    world = core.SpatialWorld([core.RobotSpec(m, base)], obstacles)
+    n, k = 60_000, 8
+    b = RoadmapBuilder(world, 0, "fk", k, 20, 0.05, flags=CHECK_OBSTACLES, single_rank=True)
+    out = b.build(n, seed=12, k2=6)
+    q = _np(out["q64"])
+    idx, dist, free = _np(out["idx"]), _np(out["dist"]), _np(out["edge_free"]).astype(bool)
+    ck = SphereChecker([m], [base], obstacles)
+    rng = np.random.default_rng(6)
+    some = rng.choice(n, 1500, replace=False)
+    assert ck.config_collision(q[some], 0, self_=False).sum() <= 2
+    # FK metric of the reference's definition on this chain: sum over all frames of the origin distances
+    P = chain.chain_frames(model_origins(m), q, base)[:, :, :3, 3]            # [n, 8, 3], float64 oracle
+    sel = np.sort(rng.choice(n, 1024, replace=False))
+    frac = check_neighbours(torch.from_numpy(np.ascontiguousarray(P)).to(cuda), sel, idx, dist, k, grouped=True)
+    assert frac < 0.01
+    rows = rng.choice(n, 80, replace=False)
+    eref = ~ck.edge_collision(np.repeat(q[rows], k, 0), q[idx[rows].ravel()], 20, 0.05, 0, self_=False)
+    assert (free[rows].ravel() != eref).sum() <= 3
+    # the accepted adjacency is the sequential pass on these tables
+    adj, deg = core.greedy_degree_connect(idx, free.astype(np.uint8), 6)
+    assert (_np(out["adj"]) == adj).all() and (_np(out["deg"]) == deg).all()
+    world.close()
