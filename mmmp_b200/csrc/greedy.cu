@@ -50,8 +50,7 @@ struct GreedyArgs {
     int32_t* in_cursor;      // [N]
     int32_t* in_ev;          // [sum in_cnt] slots of the incoming events, time order per node
     unsigned char* done;     // [N]
-    unsigned long long* changed;  // [max_rounds] per-round change counters
-    int max_rounds;
+    unsigned long long* changed;  // [3] change counters, used in rotation (round r adds to changed[r % 3])
     int32_t* rounds_out;     // device scalar
     int32_t* adj;            // [N, cap]
     int32_t* deg;            // [N]
@@ -129,8 +128,10 @@ __device__ __forceinline__ void for_events_of(const GreedyArgs& A, int64_t v, F&
 __global__ void __launch_bounds__(256) greedy_rounds_kernel(GreedyArgs A) {
     cg::grid_group grid = cg::this_grid();
     const int k2 = A.k2;
+    // Every round decides at least the earliest undecided event, so the loop ends; a chain of events
+    // that each wait for the previous one (a path graph with k2 = 1) takes as many rounds as it is long.
     int round = 0;
-    for (; round < A.max_rounds; ++round) {
+    for (;; ++round) {
         unsigned changed = 0;
         for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < A.N; v += (int64_t)gridDim.x * blockDim.x) {
             if (A.done[v]) continue;
@@ -170,9 +171,12 @@ __global__ void __launch_bounds__(256) greedy_rounds_kernel(GreedyArgs A) {
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
-        if ((threadIdx.x & 31) == 0 && changed) atomicAdd(A.changed + round, (unsigned long long)changed);
+        if ((threadIdx.x & 31) == 0 && changed) atomicAdd(A.changed + round % 3, (unsigned long long)changed);
         grid.sync();
-        if (__ldcg(A.changed + round) == 0ull) break;
+        if (__ldcg(A.changed + round % 3) == 0ull) break;
+        // the counter of round r + 2 was last read after the barrier of round r - 1 and is next written
+        // after the barrier of round r + 1: safe to clear between this barrier and the next
+        if (blockIdx.x == 0 && threadIdx.x == 0) __stcg(A.changed + (round + 2) % 3, 0ull);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.rounds_out) *A.rounds_out = round + 1;
 }
@@ -208,12 +212,12 @@ extern "C" int mmmp_greedy_degree_connect_device(const int32_t* nbr_idx_d, const
     MMMP_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return MMMP_ERR_LIMIT;
     const int64_t slots = N * k1;
-    constexpr int MAX_ROUNDS = 4096;
+    constexpr int N_COUNTERS = 3;   // change counters of the rounds, used in rotation
     // one allocation: state | side_i | side_j | done | pad | in_cnt | in_cursor | changed | in_off | in_ev
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_state = 0, o_si = up(o_state + slots), o_sj = up(o_si + slots), o_done = up(o_sj + slots);
     const size_t o_cnt = up(o_done + N), o_cur = up(o_cnt + 4 * N), o_chg = up(o_cur + 4 * N);
-    const size_t o_off = up(o_chg + 8 * MAX_ROUNDS), o_ev = up(o_off + 8 * (N + 1)), total = up(o_ev + 4 * slots);
+    const size_t o_off = up(o_chg + 8 * N_COUNTERS), o_ev = up(o_off + 8 * (N + 1)), total = up(o_ev + 4 * slots);
     unsigned char* buf = nullptr;
     MMMP_CUDA_TRY(cudaMallocAsync(&buf, total, s));
     cudaMemsetAsync(buf + o_done, 0, o_off - o_done, s);   // done, in_cnt, in_cursor, changed
@@ -233,7 +237,6 @@ extern "C" int mmmp_greedy_degree_connect_device(const int32_t* nbr_idx_d, const
     A.changed = reinterpret_cast<unsigned long long*>(buf + o_chg);
     A.in_off = reinterpret_cast<const int64_t*>(buf + o_off);
     A.in_ev = reinterpret_cast<int32_t*>(buf + o_ev);
-    A.max_rounds = MAX_ROUNDS;
     A.rounds_out = rounds_d;
     A.adj = adj_d;
     A.deg = deg_d;

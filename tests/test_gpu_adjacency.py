@@ -79,6 +79,22 @@ def test_greedy_rounds_equal_sequential_pass(core, cuda, n, k1, k2, pfree):
     assert 1 <= rounds < 200
 
 
+def test_greedy_rounds_on_a_dependency_chain(core, cuda):
+    """Worst case for the round structure: nodes on a line, candidates = the two line neighbours,
+    k2 = 1.  Node 0 takes node 1; node 1 is then full; node 2 must wait for that to know that it
+    may take node 3; ... every decision hangs on the previous one, so the pass needs thousands of
+    rounds -- and must still end with the sequential result (the round loop is unbounded)."""
+    n = 20000
+    idx = np.stack([np.arange(n) - 1, np.arange(n) + 1], 1).astype(np.int32)
+    idx[idx >= n] = -1
+    free = np.ones_like(idx, dtype=np.uint8)
+    adj, deg, rounds = core.greedy_degree_connect_device(torch.from_numpy(idx).to(cuda), torch.from_numpy(free).to(cuda),
+                                                         1, 1, return_rounds=True)
+    ref = _oracle_adj(idx, free, 1, 1)
+    assert (_np(adj) == ref).all() and rounds > 4096
+    assert (_np(deg) == 1).all() and (_np(adj)[0::2, 0] == np.arange(1, n, 2)).all()
+
+
 def test_greedy_matches_reference_golden(core, golden, cuda):
     """The reference's own connect_nearest_neighbors_degree output (production method run unbound
     on 300 Panda samples, tools/gen_golden.py): candidates from the golden k-NN table, all
