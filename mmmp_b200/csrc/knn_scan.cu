@@ -351,6 +351,38 @@ tile_box_kernel(const float* __restrict__ packed, int W, int nd, int cstride, in
     }
 }
 
+// Launch order of the query blocks of a self search, heaviest first.  A block's cost is the number
+// of tiles it loads, which grows with the size of its own bounding box (= the box of the tile that
+// holds the same rows): a block of outliers loads ten times the average (2682 tiles against 191 at
+// 1 M rows) and, scheduled late, is the tail of the launch -- the whole of it when a rank only scans
+// an eighth of the blocks.  CTAs start in blockIdx order, so handing out the big boxes first is
+// longest-processing-time-first scheduling.  One CTA: bucket the blocks by box size (64 buckets of the
+// extent sum, log scale), counting sort, largest bucket first; order inside a bucket is arbitrary
+// (it changes when a block runs, never what it computes).
+__global__ void __launch_bounds__(1024)
+block_order_kernel(const float* __restrict__ boxes, int qblock0, int n_qblocks, int32_t* __restrict__ order) {
+    __shared__ int hist[64], start[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [&](int b) {
+        const float* x = boxes + (size_t)(qblock0 + b) * 6;
+        const float e = (x[3] - x[0]) + (x[4] - x[1]) + (x[5] - x[2]);
+        int k = 63 - (int)(4.f * (log2f(fmaxf(e, 1e-9f)) + 8.f));   // 4 buckets per octave, larger extent = earlier bucket
+        return min(max(k, 0), 63);
+    };
+    for (int b = threadIdx.x; b < n_qblocks; b += blockDim.x) atomicAdd(hist + bucket(b), 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < 64; ++k) {
+            start[k] = acc;
+            acc += hist[k];
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_qblocks; b += blockDim.x) order[atomicAdd(start + bucket(b), 1)] = qblock0 + b;
+}
+
 struct KnnArgs {
     const float* pref;     // packed filter rows of the references [n_ref, W], scan order
     const float* pquery;   // packed filter rows of the queries [n_query, W], scan order
@@ -364,6 +396,7 @@ struct KnnArgs {
     int flags;             // 1 = exclude self, 2 = causal, 4 = queries ARE the references (same scan order)
     int tiles_per_split, n_splits;
     int qblock0;           // first query block (of LS scan positions) this launch covers
+    const int32_t* block_order;  // optional: query block of CTA x (absolute), heaviest first (NULL: qblock0 + x)
     int32_t* out_rows;     // sharded launch: compact output, row r = scan position qblock0 * LS + r;
                            // out_rows[r] = original query row (NULL: output indexed by original row)
     int32_t* out_idx;      // [n_query, n_splits, kc]
@@ -459,7 +492,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     }
 
     // ---- reference tiles of this CTA ---------------------------------------------
-    const int64_t q_first = ((int64_t)blockIdx.x + A.qblock0) * LS;
+    const int64_t q_first = (A.block_order ? (int64_t)__ldg(A.block_order + blockIdx.x) : (int64_t)blockIdx.x + A.qblock0) * LS;
     int64_t ref_end = A.n_ref;
     if (A.flags & 2) {
         const int64_t last_q = A.query_id0 + q_first + LS;  // exclusive bound on this CTA's query ids
@@ -1079,14 +1112,14 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     const bool same = (fquery == fref && xquery == xref && n_query == n_ref);
     // temporaries (library-owned, stream ordered)
     float *pref = nullptr, *pquery = nullptr, *boxes = nullptr, *xs = nullptr;
-    int32_t *perm = nullptr, *qperm = nullptr, *tmp_idx = nullptr;
+    int32_t *perm = nullptr, *qperm = nullptr, *tmp_idx = nullptr, *order = nullptr;
     int* bbox = nullptr;
     float* tmp_val = nullptr;
     const int nd = fdim < 3 ? fdim : 3;
     const size_t n_out = (size_t)n_rows * n_splits * k;
     const int64_t n_ref4 = (n_ref + 3) & ~(int64_t)3;
     auto cleanup = [&]() {
-        void* ptrs[] = {pref, same ? nullptr : pquery, boxes, xs, perm, same ? nullptr : qperm, bbox, tmp_idx, tmp_val};
+        void* ptrs[] = {pref, same ? nullptr : pquery, boxes, xs, perm, same ? nullptr : qperm, bbox, tmp_idx, tmp_val, order};
         for (void* p : ptrs)
             if (p) cudaFreeAsync(p, s);
     };
@@ -1145,6 +1178,17 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     A.perm = perm;
     A.qperm = qperm;
     A.boxes = boxes;
+    A.block_order = nullptr;
+    if (cull && same && query_id0 == 0 && (int64_t)KNN_CTHREADS * Q == KNN_TILE && n_qblocks > 1 &&
+        !getenv("MMMP_KNN_NO_ORDER")) {   // the query blocks are the tiles: their boxes are at hand
+        cudaError_t eo = cudaMallocAsync(&order, sizeof(int32_t) * n_qblocks, s);
+        if (eo != cudaSuccess) {
+            cleanup();
+            return MMMP_ERR_CUDA_BASE + (int)eo;
+        }
+        MMMP_LAUNCH(block_order_kernel, 1, 1024, 0, stream, boxes, qblock0, n_qblocks, order);
+        A.block_order = order;
+    }
     A.n_ref = n_ref;
     A.n_query = n_query;
     A.query_id0 = query_id0;
