@@ -145,3 +145,41 @@ def test_build_to_adjacency_1m(core, cuda):
     np.minimum.at(first, lab, np.arange(n))
     assert (_np(labels) == first[lab]).all()
     world.close()
+
+
+def test_roadmap_build_host_equals_device_pipeline(core, cuda):
+    """mmmp_roadmap_build_host (the reference-facing call of bench.py's e2e figure: host samples in,
+    the ROADMAP out, copies overlapped with kernels) against the device-resident pipeline pieces on
+    the same samples: accept test, candidate tables, verdicts, accepted adjacency, components --
+    with page-locked and with ordinary host buffers."""
+    from mmmp_b200._lib import CHECK_OBSTACLES, CHECK_SELF
+    from mmmp_b200.roadmap import RoadmapBuilder
+    model = core.load_model("panda_spheres")
+    base = core.base_matrix((0.665, 0, 0.01), (0, 0, 1, 0))
+    world = core.SpatialWorld([core.RobotSpec(model, base)], [core.plane((0, 0, 1), 0.0)])
+    lim = np.array(model["joint_limits"])
+    N, k1, k2 = 60_000, 10, 6
+    q64, q32 = core.sample_uniform(lim[:, 0], lim[:, 1], N, seed=77)
+    q_host = _np(q64)
+    # device pipeline on the same samples
+    hit = world.collide_configs(q32, 0, CHECK_SELF | CHECK_OBSTACLES)
+    keep = core.compact_free(hit)
+    n64 = core.gather_rows(q64, keep)
+    b = RoadmapBuilder(world, 0, "fk", k1, 50, 0.02, single_rank=True)
+    out = b.candidates(n64, core.pack_f32(n64))
+    b.adjacency(out, k2)
+    n = n64.shape[0]
+    for pinned in (True, False):
+        bufs = core.host_buffers(N, k1, k2, pinned=pinned)
+        res = world.roadmap_build_host(q_host, 0, core.METRIC_GROUP_L2_SUM, k1, k2, 50, 0.02, out=bufs)
+        assert res["n_nodes"] == n and (res["node_src"] == _np(keep)).all()
+        assert (res["nbr_idx"] == _np(out["idx"])).all() and (res["nbr_dist"] == _np(out["dist"])).all()
+        assert (res["edge_free"] == _np(out["edge_free"])).all()
+        assert (res["adj"] == _np(out["adj"])).all() and (res["deg"] == _np(out["deg"])).all()
+        assert (res["labels"] == _np(out["labels"])).all() and res["n_components"] == int(out["n_components"].item())
+        t = res["timings_ms"]
+        assert t[7] > 0 and t[8] > 0 and t[9] > 0 and abs(t[:6].sum() + t[8] + t[9] + t[6] - t[7]) < 0.2 * t[7] + 0.5
+    # the candidates-only entry point returns the same tables
+    res2 = world.roadmap_candidates_host(q_host, 0, core.METRIC_GROUP_L2_SUM, k1, 50, 0.02)
+    assert (res2["nbr_idx"] == _np(out["idx"])).all() and (res2["edge_free"] == _np(out["edge_free"])).all()
+    world.close()
