@@ -210,6 +210,20 @@ def kernel_counters(core, builder, args):
         return None
 
 
+def limiter(all_phases, teams):
+    """Names what holds a multi-GPU step up: the rank with the longest step, its largest phases, and
+    the time the ranks of a team spend on work that does not shrink with the team (replicated on
+    every rank of it or spent in the exchanges)."""
+    totals = [sum(p.values()) for p in all_phases]
+    slow = int(np.argmax(totals))
+    top = sorted(all_phases[slow].items(), key=lambda kv: -kv[1])[:3]
+    fixed = ("sample", "features", "accept_pass", "components", "gather_samples", "gather_adjacency", "handover_to_rank0")
+    return {"slowest_rank": slow, "its_ms": round(totals[slow], 3), "its_largest_phases": top,
+            "team_size": len(teams.ranks_of_arm[0]),
+            "ms_not_shrinking_with_the_team": round(sum(all_phases[slow].get(k_, 0.0) for k_ in fixed), 3),
+            "spread_between_ranks_ms": round(max(totals) - min(totals), 3)}
+
+
 def csv_row(learning_time_s, n_nodes, deg_sum, max_edge_len=None):
     """One row of the reference's experiment CSV schema (experiments/pybullet/exp_scalability.py:300-350)."""
     n_edges = int(deg_sum) // 2
@@ -527,6 +541,7 @@ def run_ours(args):
             "configs_checked_per_s_upper": value * 50,
             "phases_ms_per_step_rank0": {k_: v / args.steps for k_, v in phases.items()},
             "phases_ms_per_step_all_ranks": all_phases if world_size > 1 else None,
+            "limiter": limiter(all_phases, teams) if world_size > 1 else None,
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te[0]) / args.steps,

@@ -58,6 +58,14 @@ def test_arm_layout_and_csv_row():
     for ws in (1, 2, 3, 4, 8, 16):                           # every rank has work, every arm an owner
         lay = arm_layout(ws, 4)
         assert set(r for ranks in lay for r in ranks) == set(range(ws))
+    class Teams:
+        ranks_of_arm = arm_layout(4, 2)
+    lim = bench.limiter([{"knn_scan": 10.0, "edge_collision": 8.0, "accept_pass": 1.0},
+                         {"knn_scan": 12.0, "edge_collision": 8.5, "accept_pass": 1.0, "gather_adjacency": 2.0},
+                         {"knn_scan": 9.0, "edge_collision": 8.0, "accept_pass": 1.0},
+                         {"knn_scan": 9.5, "edge_collision": 8.0, "accept_pass": 1.0}], Teams)
+    assert lim["slowest_rank"] == 1 and lim["its_largest_phases"][0] == ("knn_scan", 12.0) and lim["team_size"] == 2
+    assert lim["ms_not_shrinking_with_the_team"] == 3.0 and lim["spread_between_ranks_ms"] == 5.5
     row = bench.csv_row(0.25, 1000, 9000, 0.6)
     assert row == {"learning_time": 0.25, "n_nodes": 1000, "n_edges": 4500, "avg_degree": 9.0, "max_edge_len": 0.6}
 
