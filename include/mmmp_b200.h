@@ -227,6 +227,30 @@ int mmmp_collide_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
 int mmmp_collide_segments(const mmmp_world* w, int robot, const void* qa_d, const void* qb_d,
                           int ld, int64_t E, int n_steps, double step,
                           uint32_t flags, uint8_t* out_d, void* stream);
+/* The verdicts of a whole candidate table: what connect_nearest_neighbors_degree
+ * asks of is_collision_free_edge (decoupled_prm.py:496-503) for the slots of
+ * rows [row_lo, row_hi) of nbr_d [n, k] (-1 = empty slot), spatial worlds.
+ * free_d [row_hi - row_lo, k]: 1 = edge row -> neighbour collision free, 0 = not
+ * (or empty slot).  When i and j name each other, the reference's two checks
+ * i -> j and j -> i walk the same configurations (the t grid of :859 is symmetric
+ * when n_steps * step == 1; the extra end point is a free node), so the pair is
+ * evaluated ONCE, from the lower id to the higher -- the first of the reference's
+ * two checks -- and both slots receive that verdict; every other slot is
+ * evaluated row -> neighbour.  share_across_rows == 0: only pairs with both rows
+ * inside [row_lo, row_hi) share an evaluation, free_d comes back complete.
+ * share_across_rows != 0 (several ranks, each with a block of rows): the pair's
+ * evaluation belongs to one of its two rows wherever that row lives; slots whose
+ * verdict another row holds come back as 2 and are filled in by
+ * mmmp_resolve_knn_edges on the gathered table.  Verdicts do not depend on how
+ * the rows are cut.  n_steps * step != 1: nothing is shared.                 */
+int mmmp_collide_knn_edges(const mmmp_world* w, int robot, const void* q_d, int ld,
+                           const int32_t* nbr_d, int64_t n, int k, int64_t row_lo,
+                           int64_t row_hi, int share_across_rows, int n_steps, double step,
+                           uint32_t flags, uint8_t* free_d, void* stream);
+/* free_d [row_hi - row_lo, k] (rows [row_lo, row_hi) of the table): every slot
+ * marked 2 takes the verdict of its partner's slot (both rows inside the block) */
+int mmmp_resolve_knn_edges(const int32_t* nbr_d, int64_t n, int k, int64_t row_lo,
+                           int64_t row_hi, uint8_t* free_d, void* stream);
 /* profiling aid: enable != 0 turns on four device counters of the spatial edge
  * kernels (edges seen, configurations evaluated by the step-skipping pass,
  * edges deferred to the warp-per-edge pass, configurations evaluated there);

@@ -123,6 +123,8 @@ SIGNATURES = {
                     _I64, _P, _P, _P, _P, _P],
     "mmmp_exclusive_scan_i32": [_P, _I64, _P, _P],
     "mmmp_edges_from_knn": [_P, _I64, _I, _P, _P],
+    "mmmp_collide_knn_edges": [_P, _I, _P, _I, _P, _I64, _I, _I64, _I64, _I, _I, _D, _U32, _P, _P],
+    "mmmp_resolve_knn_edges": [_P, _I64, _I, _I64, _I64, _P, _P],
     "mmmp_roadmap_candidates_host": [_P, _I, _P, _I64, _I, _I, _I, _I, _D, _U32, _P, _P, _P, _P, _P, _P],
     "mmmp_roadmap_build_host": [_P, _I, _P, _I64, _I, _I, _I, _I, _I, _D, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "mmmp_greedy_degree_connect": [_P, _P, _I64, _I, _I, _I, _P, _P],

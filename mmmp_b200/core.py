@@ -589,6 +589,31 @@ class SpatialWorld(_World):
     def dof(self) -> int:
         return int(_lib.load().mmmp_world_dof(self.handle))
 
+    def collide_knn_edges(self, q32: torch.Tensor, nbr: torch.Tensor, n_steps: int, step: float, robot: int = -1,
+                          flags: int = CHECK_SELF | CHECK_OBSTACLES, rows=None, share_across_rows: bool = False):
+        """Verdicts of a candidate table: free [hi - lo, k] uint8 for rows [lo, hi) of nbr [n, k]
+        (1 = edge row -> neighbour collision free).  A pair of nodes that name each other is evaluated
+        once, from the lower id to the higher (mmmp_collide_knn_edges); with share_across_rows the
+        slots whose verdict another row block holds come back as 2 -- resolve_knn_edges() on the
+        gathered table fills them in."""
+        q32, nbr = _dev(q32, torch.float32), _dev(nbr, torch.int32)
+        n, k = nbr.shape
+        lo, hi = (0, n) if rows is None else rows
+        free = torch.empty((hi - lo, k), dtype=torch.uint8, device=nbr.device)
+        _lib.call("mmmp_collide_knn_edges", self.handle, robot, _ptr(q32), q32.shape[1], _ptr(nbr), n, k, lo, hi,
+                  1 if share_across_rows else 0, n_steps, C.c_double(step), flags, _ptr(free), _stream())
+        return free
+
+    @staticmethod
+    def resolve_knn_edges(nbr: torch.Tensor, free: torch.Tensor, rows=None):
+        """In place: slots of `free` marked 2 take their partner's verdict (rows [lo, hi) of the table)."""
+        nbr = _dev(nbr, torch.int32)
+        n, k = nbr.shape
+        lo, hi = (0, n) if rows is None else rows
+        assert free.dtype == torch.uint8 and free.is_contiguous() and free.shape == (hi - lo, k)
+        _lib.call("mmmp_resolve_knn_edges", _ptr(nbr), n, k, lo, hi, _ptr(free), _stream())
+        return free
+
     def fk(self, q32: torch.Tensor, robot: int = 0, poses: bool = False):
         q32 = _dev(q32, torch.float32)
         L = self.robots[robot].model["n_joints"] + 1

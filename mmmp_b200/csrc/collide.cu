@@ -668,7 +668,8 @@ __device__ __forceinline__ int nth_set_bit(uint64_t m, int r) {
 template <int L>
 __global__ void __launch_bounds__(128, MMMP_COLLIDE_MINB)
 collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, const float* __restrict__ qb_base,
-                              int ld, const int32_t* __restrict__ edges, int64_t E, int n_steps, double step,
+                              int ld, const int32_t* __restrict__ edges, int64_t E,
+                              const int32_t* __restrict__ E_dev, int n_steps, double step,
                               float want_scale, int hard_after, int64_t* __restrict__ hard_edge,
                               unsigned long long* __restrict__ hard_mask, unsigned long long* __restrict__ hard_count,
                               unsigned long long* __restrict__ stats, uint8_t* __restrict__ out) {
@@ -689,6 +690,10 @@ collide_edges_adaptive_kernel(SpatialArgs A, const float* __restrict__ qa_base, 
     const int warps_per_cta = blockDim.x >> 5;
     const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
     const int64_t warp_id = (int64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    if (E_dev) {  // the list was compacted on the device: only its first *E_dev entries are edges
+        const int64_t live = __ldg(E_dev);
+        E = live < E ? live : E;
+    }
     const int64_t chunk = (E + n_warps - 1) / n_warps;
     int64_t next = warp_id * chunk;
     const int64_t w_end = next + chunk < E ? next + chunk : E;
@@ -1047,7 +1052,7 @@ extern "C" int mmmp_collide_robot_pairs(const mmmp_world* w, int ra, int rb, con
 
 static int launch_edges(const mmmp_world* w, int robot, const float* qa, const float* qb, int ld,
                         const int32_t* edges, int64_t E, int n_steps, double step, uint32_t flags,
-                        uint8_t* out, void* stream) {
+                        uint8_t* out, void* stream, const int32_t* E_dev = nullptr) {
     if (n_steps < 1 || n_steps > 4096) return MMMP_ERR_ARG;
     SpatialArgs A;
     int rc = fill_args(w, robot, flags & ~(uint32_t)MMMP_CHECK_EXHAUSTIVE, A);
@@ -1092,7 +1097,7 @@ static int launch_edges(const mmmp_world* w, int robot, const float* qa, const f
             hard_count = hard_mask + E;
             cudaMemsetAsync(hard_count, 0, sizeof(unsigned long long), st);
         }
-        MMMP_LAUNCH(collide_edges_adaptive_kernel<L>, grid, block, smem, stream, A, qa, qb, ld, edges, E, n_steps,
+        MMMP_LAUNCH(collide_edges_adaptive_kernel<L>, grid, block, smem, stream, A, qa, qb, ld, edges, E, E_dev, n_steps,
                     step, want_scale, hard_after, hard_edge, hard_mask, hard_count, g_edge_stats, out);
         if (hard_edge) {
             MMMP_LAUNCH(collide_edges_hard_kernel, grid2, block2, smem2, stream, A, qa, qb, ld, edges, hard_edge,
@@ -1128,6 +1133,159 @@ extern "C" int mmmp_collide_segments(const mmmp_world* w, int robot, const void*
                                          step, flags, out, stream);
     return launch_edges(w, robot, (const float*)qa, (const float*)qb, ld, nullptr, E, n_steps, step, flags, out,
                         stream);
+}
+
+// ---------------------------------------------------------------- verdicts of a candidate table
+// The reference's accept loop (decoupled_prm.py:496-503) checks the edge node -> neighbour for every
+// candidate slot it reaches.  When i is a candidate of j AND j a candidate of i, the two checks visit
+// the same configurations: t = s*step, s = 0 .. n_steps-1 from either end is the same interior grid
+// when n_steps*step == 1 (np.arange(0, 1, local_step), :859), plus the end the walk starts from -- a
+// roadmap node, collision free by construction.  Such a pair is evaluated ONCE, from the lower node id
+// to the higher (the direction of the first of the reference's two checks: nodes are processed in id
+// order), and both slots receive that verdict.
+namespace {
+
+enum : uint8_t { SLOT_EVAL = 0, SLOT_EMPTY = 1, SLOT_SHARED = 2 };
+
+__device__ __forceinline__ int find_in_row(const int32_t* __restrict__ row, int k, int32_t what) {
+    for (int s = 0; s < k; ++s)
+        if (__ldg(row + s) == what) return s;
+    return -1;
+}
+
+// one thread per slot of rows [row_lo, row_hi): who evaluates the pair, in which direction
+__global__ void __launch_bounds__(256)
+knn_edges_classify_kernel(const int32_t* __restrict__ nbr, int k, int64_t row_lo, int64_t row_hi, int64_t win_lo,
+                          int64_t win_hi, int share, uint8_t* __restrict__ skip, int32_t* __restrict__ pair,
+                          uint8_t* __restrict__ free_out) {
+    const int64_t total = (row_hi - row_lo) * k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = row_lo + e / k;
+        const int32_t j = __ldg(nbr + row_lo * k + e);
+        uint8_t code = SLOT_EVAL;
+        int32_t a = (int32_t)i, b = j;
+        if (j < 0) {
+            code = SLOT_EMPTY;
+        } else if (share && j != i && find_in_row(nbr + (int64_t)j * k, k, (int32_t)i) >= 0) {
+            a = i < j ? (int32_t)i : j;    // mutual candidates: the reference's first check runs low -> high
+            b = i < j ? j : (int32_t)i;
+            // one of the two slots evaluates, chosen by the parity of i + j so that no block of rows
+            // ends up with more than its share; the partner must be inside the window of rows whose
+            // verdicts the caller will see
+            const int32_t owner = ((i + j) & 1) ? a : b;
+            if (owner != (int32_t)i && j >= win_lo && j < win_hi) code = SLOT_SHARED;
+        }
+        skip[e] = code;
+        pair[2 * e] = a;
+        pair[2 * e + 1] = b;
+        free_out[e] = code == SLOT_SHARED ? 2 : 0;
+    }
+}
+
+// edges[p] = pair of the p-th evaluated slot, (-1, -1) behind the last one
+__global__ void __launch_bounds__(256)
+knn_edges_emit_kernel(const int32_t* __restrict__ slots, const int32_t* __restrict__ count,
+                      const int32_t* __restrict__ pair, int64_t total, int32_t* __restrict__ edges) {
+    const int64_t live = __ldg(count);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        int2 v = make_int2(-1, -1);
+        if (p < live) v = __ldg(reinterpret_cast<const int2*>(pair) + __ldg(slots + p));
+        reinterpret_cast<int2*>(edges)[p] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+knn_edges_expand_kernel(const int32_t* __restrict__ slots, const int32_t* __restrict__ count,
+                        const uint8_t* __restrict__ hit, int64_t total, uint8_t* __restrict__ free_out) {
+    const int64_t live = __ldg(count);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total && p < live;
+         p += (int64_t)gridDim.x * blockDim.x)
+        free_out[__ldg(slots + p)] = hit[p] ? 0 : 1;
+}
+
+// slots marked 2 take the verdict of the partner's slot (never itself marked 2); the table holds rows
+// [row_lo, row_hi), both ends of a marked slot lie inside
+__global__ void __launch_bounds__(256)
+knn_edges_resolve_kernel(const int32_t* __restrict__ nbr, int k, int64_t row_lo, int64_t row_hi,
+                         uint8_t* __restrict__ free_io) {
+    const int64_t total = (row_hi - row_lo) * k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        if (free_io[e] != 2) continue;
+        const int64_t i = row_lo + e / k;
+        const int32_t j = __ldg(nbr + row_lo * k + e);
+        uint8_t v = 0;
+        if (j >= row_lo && j < row_hi) {
+            const int s = find_in_row(nbr + (int64_t)j * k, k, (int32_t)i);
+            if (s >= 0) v = free_io[(j - row_lo) * k + s];
+        }
+        free_io[e] = v == 1 ? 1 : 0;
+    }
+}
+
+int slot_grid(int64_t items) {
+    int64_t g = (items + 255) / 256;
+    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+extern "C" int mmmp_compact_free(const uint8_t* flags, int64_t N, int32_t* idx_out, int32_t* count, void* stream);
+
+extern "C" int mmmp_resolve_knn_edges(const int32_t* nbr_d, int64_t n, int k, int64_t row_lo, int64_t row_hi,
+                                      uint8_t* free_d, void* stream) {
+    if (!nbr_d || !free_d || n < 0 || k < 1 || row_lo < 0 || row_hi > n || row_lo > row_hi) return MMMP_ERR_ARG;
+    if (row_lo == row_hi) return MMMP_OK;
+    MMMP_LAUNCH(knn_edges_resolve_kernel, slot_grid((row_hi - row_lo) * k), 256, 0, stream, nbr_d, k, row_lo, row_hi,
+                free_d);
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
+}
+
+extern "C" int mmmp_collide_knn_edges(const mmmp_world* w, int robot, const void* q, int ld, const int32_t* nbr_d,
+                                      int64_t n, int k, int64_t row_lo, int64_t row_hi, int share_across_rows,
+                                      int n_steps, double step, uint32_t flags, uint8_t* free_d, void* stream) {
+    if (!w || !q || !nbr_d || !free_d || n < 0 || k < 1 || row_lo < 0 || row_hi > n || row_lo > row_hi)
+        return MMMP_ERR_ARG;
+    MMMP_CHECK_DEVICE(w);
+    if (w->kind != MMMP_WORLD_SPATIAL) return MMMP_ERR_KIND;
+    const int64_t total = (row_hi - row_lo) * k;
+    if (total == 0) return MMMP_OK;
+    if (total > 0x7fffffff) return MMMP_ERR_ARG;
+    // the two walks visit the same configurations only on a grid that is symmetric about t = 1/2
+    double sym = (double)n_steps * step - 1.0;
+    const int share = (sym < 0 ? -sym : sym) < 1e-9 && !getenv("MMMP_EDGES_NO_SHARE");
+    cudaStream_t st = (cudaStream_t)stream;
+    mmmp_pool_keep();
+    // skip [total] u8 | hit [total] u8 | count i32 (+pad) | slots [total] i32 | pair [total] int2 | edges [total] int2
+    const size_t off_hit = (size_t)((total + 15) & ~(int64_t)15);
+    const size_t off_count = 2 * off_hit, off_slots = off_count + 16;
+    const size_t off_pair = off_slots + sizeof(int32_t) * (size_t)((total + 3) & ~(int64_t)3);
+    const size_t off_edges = off_pair + sizeof(int32_t) * 2 * (size_t)total;
+    unsigned char* buf = nullptr;
+    MMMP_CUDA_TRY(cudaMallocAsync(&buf, off_edges + sizeof(int32_t) * 2 * (size_t)total, st));
+    uint8_t *skip = buf, *hit = buf + off_hit;
+    int32_t* count = reinterpret_cast<int32_t*>(buf + off_count);
+    int32_t* slots = reinterpret_cast<int32_t*>(buf + off_slots);
+    int32_t* pair = reinterpret_cast<int32_t*>(buf + off_pair);
+    int32_t* edges = reinterpret_cast<int32_t*>(buf + off_edges);
+    const int64_t win_lo = share_across_rows ? 0 : row_lo, win_hi = share_across_rows ? n : row_hi;
+    int rc = MMMP_OK;
+    MMMP_LAUNCH(knn_edges_classify_kernel, slot_grid(total), 256, 0, stream, nbr_d, k, row_lo, row_hi, win_lo, win_hi,
+                share, skip, pair, free_d);
+    rc = mmmp_compact_free(skip, total, slots, count, stream);
+    if (rc == MMMP_OK) {
+        MMMP_LAUNCH(knn_edges_emit_kernel, slot_grid(total), 256, 0, stream, slots, count, pair, total, edges);
+        rc = launch_edges(w, robot, (const float*)q, nullptr, ld, edges, total, n_steps, step, flags, hit, stream, count);
+    }
+    if (rc == MMMP_OK) {
+        MMMP_LAUNCH(knn_edges_expand_kernel, slot_grid(total), 256, 0, stream, slots, count, hit, total, free_d);
+        if (share && !share_across_rows)
+            MMMP_LAUNCH(knn_edges_resolve_kernel, slot_grid(total), 256, 0, stream, nbr_d, k, row_lo, row_hi, free_d);
+    }
+    cudaFreeAsync(buf, st);
+    if (rc != MMMP_OK) return rc;
+    MMMP_LAUNCH_CHECK();
+    return MMMP_OK;
 }
 
 #ifdef MMMP_EDGE_DIAG

@@ -21,12 +21,6 @@ edges_from_knn_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int32_t
     }
 }
 
-__global__ void __launch_bounds__(256)
-invert_flags_kernel(uint8_t* f, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        f[i] = f[i] ? 0 : 1;
-}
-
 // *out |= 1 if any byte of f is non-zero
 __global__ void __launch_bounds__(256)
 any_flag_kernel(const uint8_t* __restrict__ f, int64_t n, int* __restrict__ out) {
@@ -146,7 +140,7 @@ static int roadmap_host_impl(const mmmp_world* w, int robot, const double* q64_h
     int rc = MMMP_OK;
     int64_t n_nodes = 0;
     {
-        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, edges, ecoll, amb, adj,
+        DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, ecoll, amb, adj,
             deg, labels, ncomp;
         const int L = nj + 1;
         auto T = [&](cudaError_t e) {
@@ -182,7 +176,6 @@ static int roadmap_host_impl(const mmmp_world* w, int robot, const double* q64_h
             T(amb.alloc(((n + 3) & ~(int64_t)3) + sizeof(int)));
             T(ridx.alloc(sizeof(int32_t) * n * k));
             T(rdist.alloc(sizeof(double) * n * k));
-            T(edges.alloc(sizeof(int32_t) * n * k * 2));
             T(ecoll.alloc(n * k));
             mmmp_metric m32, m64;
             memset(&m32, 0, sizeof(m32));
@@ -262,13 +255,8 @@ static int roadmap_host_impl(const mmmp_world* w, int robot, const double* q64_h
                 T(cudaMemcpyAsync(node_src_h, idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s2));
                 T(cudaMemcpyAsync(nbr_idx_h, ridx.p, sizeof(int32_t) * n * k, cudaMemcpyDeviceToHost, s2));
                 if (nbr_dist_h) T(cudaMemcpyAsync(nbr_dist_h, rdist.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, s2));
-                R(mmmp_edges_from_knn(ridx.as<int32_t>(), n, k, edges.as<int32_t>(), s));
-                R(mmmp_collide_edges(w, robot, nq32.p, ld32, edges.as<int32_t>(), n * k, n_steps, step, flags,
-                                     ecoll.as<uint8_t>(), s));
-                int g = mmmp_div_up(n * k, 256);
-                if (g > 148 * 16) g = 148 * 16;
-                MMMP_LAUNCH(invert_flags_kernel, g, 256, 0, s, ecoll.as<uint8_t>(), n * k);
-                T(cudaPeekAtLastError());
+                R(mmmp_collide_knn_edges(w, robot, nq32.p, ld32, ridx.as<int32_t>(), n, k, 0, n, 0, n_steps, step,
+                                         flags, ecoll.as<uint8_t>(), s));
                 cudaEventRecord(ev[6], s);
                 // ... and the verdicts while the accept pass runs
                 cudaEventRecord(ready, s);

@@ -298,10 +298,10 @@ class DecoupledPRM:
         """[E] uint8: 1 where the straight edge (q32[a], q32[b]) is NOT collision free."""
         return self.env.world.collide_edges(q32, edges, self.n_steps, self.local_step, r_index, self._flags())
 
-    def _edge_free_table(self, r_index, q32, idx):
-        """[n, k] verdict of is_collision_free_edge(node_i, candidate) for a neighbour table."""
-        hit = self._edges_hit(r_index, q32, core.edges_from_knn(idx))
-        return (hit == 0).reshape(idx.shape).cpu().numpy().astype(np.uint8)
+    def _candidate_verdicts(self, r_index, q32, idx):
+        """[n, k] uint8 on the device: 1 where is_collision_free_edge(node_i, candidate) holds.  Mutual
+        candidates are checked once, low id -> high id: the first of the accept loop's two checks."""
+        return self.env.world.collide_knn_edges(q32, idx, self.n_steps, self.local_step, r_index, self._flags())
 
     def connect_nearest_neighbors_degree(self, r_id):
         """:480-504.  k1 candidates per node (all other nodes: the reference's degree filter
@@ -315,7 +315,7 @@ class DecoupledPRM:
         F = self._features(r_index, q64, q32)
         k1 = min(self.k1, len(nodes) - 1)
         idx, dist, amb = core.knn_exact(F, F, k1)
-        free_d = (self._edges_hit(r_index, q32, core.edges_from_knn(idx)) == 0).to(torch.uint8).reshape(idx.shape)
+        free_d = self._candidate_verdicts(r_index, q32, idx)
         # the order-dependent accept pass, on the device (same adjacency and list order as the
         # sequential loop: tests/test_gpu_adjacency.py)
         adj, deg = core.greedy_degree_connect_device(idx, free_d.contiguous(), self.k2)

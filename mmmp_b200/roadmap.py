@@ -312,17 +312,17 @@ class RoadmapBuilder:
                 t1.synchronize()
                 self._rebalance(t0.elapsed_time(t1))
             self._mark("gather_adjacency")
-        mine = idx[lo:hi].contiguous() if self.size > 1 else idx
-        edges = core.edges_from_knn(mine)
-        if lo > 0:
-            edges[:, 0] += lo
-        hit = self.world.collide_edges(q32, edges, self.n_steps, self.step, self.robot, self.flags)
-        free = (hit == 0).to(torch.uint8).reshape(hi - lo, self.k)
+        # a pair of nodes that name each other is evaluated once (mmmp_collide_knn_edges); across ranks
+        # the evaluation belongs to one of the two rows and the other slot is filled in after the gather
+        across = self.size > 1 and gather
+        free = self.world.collide_knn_edges(q32, idx, self.n_steps, self.step, self.robot, self.flags,
+                                            rows=(lo, hi), share_across_rows=across)
         self._mark("edge_collision")
         if self.size > 1:
             if gather:   # equal row blocks (the last may be short): rank order = row order
                 per = (n + self.size - 1) // self.size
-                free = all_gather_padded(free, per, self.size, self.group)[:n]
+                free = all_gather_padded(free, per, self.size, self.group)[:n].contiguous()
+                core.SpatialWorld.resolve_knn_edges(idx, free)
                 self._mark("gather_adjacency")
             else:
                 idx, dist, amb = idx[lo:hi], dist[lo:hi], amb[lo:hi]

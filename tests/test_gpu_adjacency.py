@@ -183,3 +183,69 @@ def test_roadmap_build_host_equals_device_pipeline(core, cuda):
     res2 = world.roadmap_candidates_host(q_host, 0, core.METRIC_GROUP_L2_SUM, k1, 50, 0.02)
     assert (res2["nbr_idx"] == _np(out["idx"])).all() and (res2["edge_free"] == _np(out["edge_free"])).all()
     world.close()
+
+
+def test_candidate_table_verdicts_share_mutual_pairs(core, cuda):
+    """mmmp_collide_knn_edges: a pair of nodes that name each other is evaluated once, low id -> high id (the
+    first of the two checks of decoupled_prm.py:496-503); every other slot row -> neighbour.  The table equals
+    mmmp_collide_edges on exactly those directed edges bit for bit, however the rows are cut across callers,
+    and nothing is shared when the t grid is not symmetric (n_steps * step != 1)."""
+    import os
+    from mmmp_b200._lib import CHECK_OBSTACLES, CHECK_SELF
+    from mmmp_b200.roadmap import RoadmapBuilder
+    F = CHECK_SELF | CHECK_OBSTACLES
+    model = core.load_model("panda_spheres")
+    world = core.SpatialWorld([core.RobotSpec(model, core.base_matrix((0, 0, 0.01)))],
+                              [core.plane((0, 0, 1), 0.0), core.box((0.45, 0.0, 0.3), (0.08, 0.3, 0.3))])
+    n, k = 30_000, 10
+    b = RoadmapBuilder(world, 0, "fk", k, 50, 0.02, single_rank=True)
+    q64, q32 = b.sample_free(n, seed=3)
+    feats = b.features(q64, q32)
+    idx, _, _ = core.knn_exact(feats, feats, k)
+    idx[17, 4] = -1                                       # an empty slot
+    nbr = _np(idx).astype(np.int64)
+    rows = np.repeat(np.arange(n), k).reshape(n, k)
+    valid = nbr >= 0
+    mutual = np.zeros((n, k), bool)
+    mutual[valid] = (nbr[nbr[valid]] == rows[valid][:, None]).any(1)
+    assert 0.2 < mutual.mean() < 0.9
+    a = np.where(mutual, np.minimum(rows, nbr), rows)
+    c = np.where(mutual, np.maximum(rows, nbr), nbr)
+
+    def directed(a, c, n_steps, step):
+        e = torch.from_numpy(np.stack([a.ravel(), c.ravel()], 1).astype(np.int32)).to(cuda)
+        return (_np(world.collide_edges(q32, e, n_steps, step, 0, F)) == 0).reshape(n, k).astype(np.uint8)
+
+    want = directed(a, c, 50, 0.02)
+    assert 0.03 < 1.0 - want.mean() < 0.9
+    got = _np(world.collide_knn_edges(q32, idx, 50, 0.02, 0, F))
+    assert (got == want).all() and got[17, 4] == 0
+    # both slots of a mutual pair agree by construction
+    j = nbr[mutual]
+    s_back = (nbr[j] == rows[mutual][:, None]).argmax(1)
+    assert (got[mutual] == got[j, s_back]).all()
+    # row blocks of several callers: partners inside the block only ...
+    cuts = [0, 9_000, 9_001, 22_222, n]
+    parts = [_np(world.collide_knn_edges(q32, idx, 50, 0.02, 0, F, rows=(lo, hi))) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    assert (np.concatenate(parts) == want).all()
+    # ... or anywhere, resolved on the gathered table; every pair is evaluated by exactly one block
+    parts = [world.collide_knn_edges(q32, idx, 50, 0.02, 0, F, rows=(lo, hi), share_across_rows=True)
+             for lo, hi in zip(cuts[:-1], cuts[1:])]
+    table = torch.cat(parts).contiguous()
+    marked = _np(table) == 2
+    assert marked.any() and not (marked & ~mutual).any()
+    assert (marked[mutual] != marked[j, s_back]).all(), "exactly one slot of a mutual pair is evaluated"
+    core.SpatialWorld.resolve_knn_edges(idx, table)
+    assert (_np(table) == want).all()
+    # a grid that is not symmetric shares nothing: every slot row -> neighbour
+    for n_steps, step in ((7, 0.15), (20, 0.04)):
+        assert (_np(world.collide_knn_edges(q32, idx, n_steps, step, 0, F)) == directed(rows, nbr, n_steps, step)).all()
+    # and the shared evaluation differs from two separate ones by rounding at most (same configurations)
+    os.environ["MMMP_EDGES_NO_SHARE"] = "1"
+    try:
+        plain = _np(world.collide_knn_edges(q32, idx, 50, 0.02, 0, F))
+    finally:
+        del os.environ["MMMP_EDGES_NO_SHARE"]
+    assert (plain == directed(rows, nbr, 50, 0.02)).all()
+    assert (plain != want).sum() <= 5
+    world.close()

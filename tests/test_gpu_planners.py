@@ -187,6 +187,10 @@ def test_decoupled_connect_methods_equal_reference(cuda, golden):
             hit = [(int(round((q[a].sum() + q[b].sum()) * 100)) % 7) == 0 for a, b in e]   # tools/gen_golden.py ef()
             return torch.tensor(hit, dtype=torch.uint8, device=q32.device)
 
+        def _candidate_verdicts(self, r_index, q32, idx):
+            from mmmp_b200 import core
+            return (self._edges_hit(r_index, q32, core.edges_from_knn(idx)) == 0).to(torch.uint8).reshape(idx.shape)
+
     p = Probe.__new__(Probe)
     p.env, p.agents, p.robot_models, p.obstacles = env, env.agents, env.robot_models, env.obstacles
     p.r_ids = [m.r_id for m in env.robot_models]

@@ -2,11 +2,12 @@
 """One launch of one kernel of the path at the bench size, for ncu (profile_r02.sh) -- and, run
 without ncu, the library's own work counters of that launch as a line `COUNTERS {json}`:
 
-    python tools/kernel_probe.py scan|scan14|edge|configs|fk|accept [n]
+    python tools/kernel_probe.py scan|scan14|edge|knnedge|configs|fk|accept [n]
 
 scan    knn_scan_kernel<1,1>: 1 M x 1 M FK-metric self search, 12 candidates (the bench launch)
 scan14  knn_scan_kernel<4,1>: 200 k composite 14-D rows, L2, 12 candidates (C4)
 edge    collide_edges_adaptive_kernel<4> + collide_edges_hard_kernel on the 10 M candidate edges
+knnedge mmmp_collide_knn_edges on the same table: mutual candidates evaluated once (the bench's call)
 configs collide_configs_kernel on 2 M uniform samples (the accept test of the sampler)
 fk      fk_chain_kernel on 1 M configurations (positions only)
 accept  the greedy accept pass + components on the candidate tables of one arm
@@ -44,7 +45,7 @@ def timed(fn):
 
 
 counters = {"what": what, "n": n}
-if what in ("scan", "edge", "accept", "configs", "fk"):
+if what in ("scan", "edge", "knnedge", "accept", "configs", "fk"):
     world = core.SpatialWorld([core.RobotSpec(model, bases[0], 0)], obstacles)
     b = RoadmapBuilder(world, 0, "fk", 10, 50, 0.02, single_rank=True)
     if what == "configs":
@@ -79,9 +80,17 @@ if what in ("scan", "edge", "accept", "configs", "fk"):
                 L.mmmp_edge_stats(0, None)
                 counters.update(ms=ms, edges=int(es[0]), evals_adaptive=int(es[1]), deferred=int(es[2]), evals_hard=int(es[3]),
                                 blocked=float(hit.float().mean()))
+            elif what == "knnedge":   # the bench's call: mutual candidates evaluated once
+                world.collide_knn_edges(q32, idx, 50, 0.02, 0, F)
+                L.mmmp_edge_stats(1, None)
+                free, ms = timed(lambda: world.collide_knn_edges(q32, idx, 50, 0.02, 0, F))
+                es = (C.c_ulonglong * 4)()
+                L.mmmp_edge_stats(1, es)
+                L.mmmp_edge_stats(0, None)
+                counters.update(ms=ms, slots=int(idx.numel()), edges=int(es[0]), evals_adaptive=int(es[1]), deferred=int(es[2]),
+                                evals_hard=int(es[3]), blocked=1.0 - float(free.float().mean()))
             else:
-                hit = world.collide_edges(q32, edges, 50, 0.02, 0, F)
-                free = (hit == 0).to(torch.uint8).reshape(n, 10)
+                free = world.collide_knn_edges(q32, idx, 50, 0.02, 0, F)
                 (adj, deg, rounds), ms = timed(lambda: core.greedy_degree_connect_device(idx, free, 10, return_rounds=True))
                 (labels, count), ms2 = timed(lambda: core.connected_components(adj))
                 counters.update(ms=ms, rounds=rounds, components_ms=ms2, mean_degree=float(deg.float().mean()),
