@@ -506,6 +506,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
     // ---- queries: filter form in registers (a2 = -2 x, last column of the packed row = A_q),
     //      exact row in this thread's shared-memory column ----
     float a2[Q][W], thr[Q], thr1[Q], Aq[Q], Aq1[Q], tauf[Q];
+    float2 nthr2[Q];  // DUAL: (-thr1, -(thr - thr1)), added to (accC, accD) by one packed FADD2
     int64_t qrow[Q];
     if (tid < KNN_CTHREADS) {
         float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -534,6 +535,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
             }
             thr[qq] = valid ? CUDART_INF_F : -CUDART_INF_F;
             thr1[qq] = thr[qq];
+            nthr2[qq] = make_float2(-thr[qq], -thr[qq]);
             tauf[qq] = valid ? CUDART_INF_F : 0.f;
             qrow[qq] = valid ? (A.qperm ? (int64_t)__ldg(A.qperm + qi) : qi) : 0;
             for (int c = 0; c < S; ++c)
@@ -767,6 +769,7 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                 const float tf = ((A.M.kind == MMMP_METRIC_GROUP_L2_SUM) ? tau * tau : tau) * (1.f + KNN_SLACK);
                 thr[qq] = (DUAL ? 2.f * tf : tf) - Aq[qq];
                 thr1[qq] = tf - Aq1[qq];
+                nthr2[qq] = make_float2(-thr1[qq], -(thr[qq] - thr1[qq]));
                 tauf[qq] = tf;
             }
             worst = fmaxf(worst, tauf[qq]);
@@ -837,7 +840,11 @@ knn_scan_kernel(const __grid_constant__ KnnArgs A) {
                             acc = __ffma2_rn(make_float2(a2[qq][0], a2[qq][1]), make_float2(r[u][0].x, r[u][0].y), acc);
                             acc = __ffma2_rn(make_float2(a2[qq][2], a2[qq][3]), make_float2(r[u][0].z, r[u][0].w), acc);
                             acc = __ffma2_rn(make_float2(a2[qq][4], a2[qq][5]), make_float2(r[u][F4 - 1].x, r[u][F4 - 1].y), acc);
-                            sv[qq][u] = fmaxf(acc.x - thr1[qq], acc.x + acc.y - thr[qq]);
+                            // both tests from one packed add: t = (sC - thr1, sD - (thr - thr1)); the second
+                            // test reads t.x + t.y (rounding differs from sC + sD - thr by ulps, far inside
+                            // the filter's slack)
+                            const float2 t = __fadd2_rn(acc, nthr2[qq]);
+                            sv[qq][u] = fmaxf(t.x, t.x + t.y);
                         } else if (F4 >= 2) {
                             // even and odd columns accumulate in the two halves of a packed FFMA2 (the
                             // norm column enters with multiplier 1): half the FMA instructions
