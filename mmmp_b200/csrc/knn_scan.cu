@@ -13,8 +13,8 @@
 // both in the scan order, so that a tile of either is one contiguous block.
 //
 // Spatial ordering + exact tile culling (non-causal searches with >= 4096 references):
-// rows are counting-sorted by the Morton code of their grid cell (first three filter
-// dimensions), so that a shared-memory tile of 128 consecutive rows and a CTA's 128*Q
+// rows are counting-sorted by the position of their grid cell on the 3-D Hilbert curve (first
+// three filter dimensions), so that a shared-memory tile of 128 consecutive rows and a CTA's 128*Q
 // consecutive queries are both spatially compact; every tile carries its bounding box.
 // The producer warp walks the tiles outward from the CTA's own position, 32 boxes per
 // step, and only loads a tile whose box is closer to the CTA's query box than the CTA's
@@ -219,17 +219,54 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
     return v;
 }
 
-// Morton cell of a row (bits per axis = `bits`) in the box `bbox`
+#ifndef MMMP_KNN_HILBERT
+#define MMMP_KNN_HILBERT 1
+#endif
+// Position of the grid cell (x0, x1, x2), `bits` bits per axis, on the 3-D Hilbert curve (Skilling's
+// transpose algorithm, AIP Conf. Proc. 707, 2004).  Consecutive cells of the curve share a face, so a
+// run of rows -- a tile, a CTA's query block -- never straddles one of the Z curve's jumps: the run's
+// bounding box stays close to the cells it covers.
+__device__ __forceinline__ uint32_t hilbert3(uint32_t x0, uint32_t x1, uint32_t x2, int bits) {
+    uint32_t X[3] = {x0, x1, x2};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t;
+    X[1] ^= t;
+    X[2] ^= t;
+    return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
+}
+
+// Cell of a row (bits per axis = `bits`) in the box `bbox`, numbered along the Hilbert curve (three
+// sort dimensions) or the Z curve (fewer)
 __device__ __forceinline__ uint32_t cell_of(const float* row, int nd, const int* bbox, int bits) {
-    uint32_t key = 0;
+    uint32_t key = 0, v3[3] = {0, 0, 0};
     const float cells = (float)(1 << bits);
     for (int c = 0; c < nd; ++c) {
         const float lo = ordered_float(bbox[c]), hi = ordered_float(bbox[3 + c]);
         const float ext = hi - lo;
         int v = ext > 0.f ? (int)((row[c] - lo) / ext * cells) : 0;
         v = min(max(v, 0), (1 << bits) - 1);
+        v3[c] = (uint32_t)v;
         key |= spread3((uint32_t)v) << c;
     }
+    if (MMMP_KNN_HILBERT && nd == 3) key = hilbert3(v3[0], v3[1], v3[2], bits);
     return key;
 }
 
@@ -351,6 +388,11 @@ tile_box_kernel(const float* __restrict__ packed, int W, int nd, int cstride, in
     }
 }
 
+// (Opt-in since the rows follow the Hilbert curve, MMMP_KNN_ORDER=1: the outlier blocks this was written
+// for were runs that straddled a jump of the Z curve -- 3033 tiles for one block against a mean of 191;
+// along the Hilbert curve the heaviest block loads 333, and launching neighbouring blocks together
+// (shared tiles in L2) is worth more than the schedule: 1 M rows 19.0 ms with, 18.4 ms without; half
+// the blocks on one rank 10.6 against 10.1 ms.)
 // Launch order of the query blocks of a self search, heaviest first.  A block's cost is the number
 // of tiles it loads, which grows with the size of its own bounding box (= the box of the tile that
 // holds the same rows): a block of outliers loads ten times the average (2682 tiles against 191 at
@@ -996,7 +1038,7 @@ int grid_for(int64_t n, int sms) {
     return g > sms * 16 ? sms * 16 : (g < 1 ? 1 : g);
 }
 
-// counting sort of rows by Morton cell: perm[pos] = original row
+// counting sort of rows by grid cell along the Hilbert curve: perm[pos] = original row
 int spatial_perm(const float* rows, int ld, int nd, int64_t n, const int* bbox_d, int bits, int32_t* perm,
                  void* stream, int sms) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -1144,9 +1186,11 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     KNN_TRY(cudaMallocAsync(&tmp_idx, n_out * sizeof(int32_t), s));
     KNN_TRY(cudaMallocAsync(&tmp_val, n_out * sizeof(float), s));
     if (cull) {
-        // grid resolution: ~16 rows per cell, 1..7 bits per axis
+        // grid resolution: 2..16 rows per cell, 1..7 bits per axis (measured with the Hilbert order, 1 M rows:
+        // 4 / 5 / 6 / 7 bits -> 28.6 / 19.6 / 19.0 / 19.0 ms; rows of one cell are in row order, so a finer
+        // grid makes the runs more compact until a cell holds a handful of rows)
         int bits = 1;
-        while (bits < 7 && ((int64_t)1 << (3 * (bits + 1))) * 16 <= n_ref) ++bits;
+        while (bits < 7 && ((int64_t)1 << (3 * (bits + 1))) * 2 <= n_ref) ++bits;
         if (const char* e = getenv("MMMP_KNN_BITS")) bits = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
         KNN_TRY(cudaMallocAsync(&bbox, 6 * sizeof(int), s));
         const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
@@ -1187,7 +1231,7 @@ static int knn_impl(const float* fref, const float* xref, int64_t n_ref, const f
     A.boxes = boxes;
     A.block_order = nullptr;
     if (cull && same && query_id0 == 0 && (int64_t)KNN_CTHREADS * Q == KNN_TILE && n_qblocks > 1 &&
-        !getenv("MMMP_KNN_NO_ORDER")) {   // the query blocks are the tiles: their boxes are at hand
+        getenv("MMMP_KNN_ORDER")) {   // the query blocks are the tiles: their boxes are at hand
         cudaError_t eo = cudaMallocAsync(&order, sizeof(int32_t) * n_qblocks, s);
         if (eo != cudaSuccess) {
             cleanup();
