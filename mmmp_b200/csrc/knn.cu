@@ -13,6 +13,7 @@
 // single_arm/distance_prm.py:40-52,126; metrics robots/panda.py:248-254,
 // robots/planar_arm.py:54-61, decoupled_prm.py:824.
 #include <math_constants.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -61,60 +62,125 @@ __device__ __forceinline__ double exact_metric_f64(int kind, int dim, int group,
     return s;
 }
 
+// one query row, one thread: candidates evaluated and insertion-sorted in turn
+__device__ void refine_serial(const double* __restrict__ ref, const double* __restrict__ query, int ld, int kind, int dim,
+                              int group, const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_dist,
+                              int64_t q, int kc, int k, double tie_eps, int32_t* __restrict__ out_idx,
+                              double* __restrict__ out_dist, uint8_t* __restrict__ ambiguous) {
+    double dv[MMMP_MAX_K];
+    int di[MMMP_MAX_K];
+    int n = 0;
+    const double* a = query + q * ld;
+    double err32 = 0.0;   // largest |fp32 scan value - float64 value| seen on this row's candidates
+    for (int c = 0; c < kc; ++c) {
+        const int id = cand_idx[(size_t)q * kc + c];
+        if (id < 0) continue;
+        const double d = exact_metric_f64(kind, dim, group, a, ref + (int64_t)id * ld);
+        if (cand_dist) err32 = fmax(err32, fabs(d - (double)cand_dist[(size_t)q * kc + c]));
+        int p = n++;
+        while (p > 0 && (dv[p - 1] > d || (dv[p - 1] == d && di[p - 1] > id))) {
+            dv[p] = dv[p - 1];
+            di[p] = di[p - 1];
+            --p;
+        }
+        dv[p] = d;
+        di[p] = id;
+    }
+    // exact float64 ties straddling rank k: the reference's bounded heap pops the
+    // smallest id first, i.e. keeps the LARGER ids (decoupled_prm.py:490-492).
+    if (n > k && dv[k] == dv[k - 1]) {
+        int lo = k - 1, hi = k;
+        while (lo > 0 && dv[lo - 1] == dv[k - 1]) --lo;
+        while (hi + 1 < n && dv[hi + 1] == dv[k - 1]) ++hi;
+        const int need = k - lo;                 // slots left for the tie group [lo, hi]
+        const int first = (hi - lo + 1) - need;  // skip this many of its smallest ids
+        for (int c = lo; c < k; ++c) {
+            dv[c] = dv[c + first];
+            di[c] = di[c + first];
+        }
+    }
+    for (int c = 0; c < k; ++c) {
+        out_idx[(size_t)q * k + c] = c < n ? di[c] : -1;
+        if (out_dist) out_dist[(size_t)q * k + c] = c < n ? dv[c] : CUDART_INF;
+    }
+    if (ambiguous) {
+        // The fp32 scan kept the kc smallest fp32 values.  A row it dropped has an fp32 value of
+        // at least vl (its kc-th); that row belongs in the float64 top k only if fp32 error can
+        // bridge the gap between vl and the float64 k-th distance.  The error is not assumed: it
+        // is measured on this row's own candidates (err32) and given a factor 4 in hand, with
+        // tie_eps as the floor (an absolute 1e-6 ignored the metric's magnitude).
+        uint8_t amb = 0;
+        if (kc > k && n >= kc) {
+            const double vl = (double)cand_dist[(size_t)q * kc + (kc - 1)];
+            if (vl - dv[k - 1] <= fmax(tie_eps, 4.0 * err32)) amb = 1;
+        }
+        ambiguous[q] = amb;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 knn_refine_kernel(const double* __restrict__ ref, const double* __restrict__ query, int ld, int kind, int dim, int group,
                   const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_dist, int64_t n_query, int kc,
                   int k, double tie_eps, int32_t* __restrict__ out_idx, double* __restrict__ out_dist,
                   uint8_t* __restrict__ ambiguous) {
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_query; q += (int64_t)gridDim.x * blockDim.x) {
-        double dv[MMMP_MAX_K];
-        int di[MMMP_MAX_K];
-        int n = 0;
-        const double* a = query + q * ld;
-        double err32 = 0.0;   // largest |fp32 scan value - float64 value| seen on this row's candidates
-        for (int c = 0; c < kc; ++c) {
-            const int id = cand_idx[(size_t)q * kc + c];
-            if (id < 0) continue;
-            const double d = exact_metric_f64(kind, dim, group, a, ref + (int64_t)id * ld);
-            err32 = fmax(err32, fabs(d - (double)cand_dist[(size_t)q * kc + c]));
-            int p = n++;
-            while (p > 0 && (dv[p - 1] > d || (dv[p - 1] == d && di[p - 1] > id))) {
-                dv[p] = dv[p - 1];
-                di[p] = di[p - 1];
-                --p;
-            }
-            dv[p] = d;
-            di[p] = id;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_query; q += (int64_t)gridDim.x * blockDim.x)
+        refine_serial(ref, query, ld, kind, dim, group, cand_idx, cand_dist, q, kc, k, tie_eps, out_idx, out_dist,
+                      ambiguous);
+}
+
+// The same answer with G lanes per query row (kc <= G): lane c evaluates candidate c -- the kc gathers
+// of a row are in flight together instead of one after the other --, ranks it among the row's
+// candidates by (distance, id) with shuffles, and the lanes of rank < k write the row.  An exact
+// float64 tie across rank k (the reference's heap rule above) sends the row to refine_serial.
+template <int G>
+__global__ void __launch_bounds__(128)
+knn_refine_group_kernel(const double* __restrict__ ref, const double* __restrict__ query, int ld, int kind, int dim,
+                        int group, const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_dist,
+                        int64_t n_query, int kc, int k, double tie_eps, int32_t* __restrict__ out_idx,
+                        double* __restrict__ out_dist, uint8_t* __restrict__ ambiguous) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
+    const int gpc = blockDim.x / G;
+    for (int64_t q = (int64_t)blockIdx.x * gpc + threadIdx.x / G; q < n_query; q += (int64_t)gridDim.x * gpc) {
+        const int id = sub < kc ? cand_idx[(size_t)q * kc + sub] : -1;
+        const bool valid = id >= 0;
+        double d = CUDART_INF;
+        if (valid) d = exact_metric_f64(kind, dim, group, query + q * ld, ref + (int64_t)id * ld);
+        double err32 = (valid && cand_dist) ? fabs(d - (double)cand_dist[(size_t)q * kc + sub]) : 0.0;
+        int rank = 0;
+        for (int o = 0; o < G; ++o) {
+            const double od = __shfl_sync(gmask, d, o, G);
+            const int oi = __shfl_sync(gmask, id, o, G);
+            rank += (oi >= 0 && (od < d || (od == d && oi < id))) ? 1 : 0;
         }
-        // exact float64 ties straddling rank k: the reference's bounded heap pops the
-        // smallest id first, i.e. keeps the LARGER ids (decoupled_prm.py:490-492).
-        int first = 0;  // take dv[0..k) but within the boundary tie group prefer larger ids
-        if (n > k && dv[k] == dv[k - 1]) {
-            int lo = k - 1, hi = k;
-            while (lo > 0 && dv[lo - 1] == dv[k - 1]) --lo;
-            while (hi + 1 < n && dv[hi + 1] == dv[k - 1]) ++hi;
-            const int need = k - lo;           // slots left for the tie group [lo, hi]
-            first = (hi - lo + 1) - need;      // skip this many of its smallest ids
-            for (int c = lo; c < k; ++c) {
-                dv[c] = dv[c + first];
-                di[c] = di[c + first];
-            }
+        const unsigned vmask = __ballot_sync(gmask, valid) & gmask;
+        const int n = __popc(vmask);
+        // the values at ranks k-1 and k (ranks are distinct among valid lanes: ids are)
+        const unsigned at_k1 = __ballot_sync(gmask, valid && rank == k - 1) & gmask;
+        const unsigned at_k = __ballot_sync(gmask, valid && rank == k) & gmask;
+        const double dk1 = __shfl_sync(gmask, d, at_k1 ? (__ffs(at_k1) - 1) % G : 0, G);
+        const double dk = __shfl_sync(gmask, d, at_k ? (__ffs(at_k) - 1) % G : 0, G);
+        for (int o = G / 2; o > 0; o >>= 1) err32 = fmax(err32, __shfl_xor_sync(gmask, err32, o, G));
+        if (at_k && at_k1 && dk == dk1) {   // tie across the cut: the sequential rule decides
+            if (sub == 0)
+                refine_serial(ref, query, ld, kind, dim, group, cand_idx, cand_dist, q, kc, k, tie_eps, out_idx,
+                              out_dist, ambiguous);
+            continue;
         }
-        (void)first;
-        for (int c = 0; c < k; ++c) {
-            out_idx[(size_t)q * k + c] = c < n ? di[c] : -1;
-            if (out_dist) out_dist[(size_t)q * k + c] = c < n ? dv[c] : CUDART_INF;
+        if (valid && rank < k) {
+            out_idx[(size_t)q * k + rank] = id;
+            if (out_dist) out_dist[(size_t)q * k + rank] = d;
         }
-        if (ambiguous) {
-            // The fp32 scan kept the kc smallest fp32 values.  A row it dropped has an fp32 value of
-            // at least vl (its kc-th); that row belongs in the float64 top k only if fp32 error can
-            // bridge the gap between vl and the float64 k-th distance.  The error is not assumed: it
-            // is measured on this row's own candidates (err32) and given a factor 4 in hand, with
-            // tie_eps as the floor (an absolute 1e-6 ignored the metric's magnitude).
+        if (sub >= n && sub < k) {
+            out_idx[(size_t)q * k + sub] = -1;
+            if (out_dist) out_dist[(size_t)q * k + sub] = CUDART_INF;
+        }
+        if (ambiguous && sub == 0) {
             uint8_t amb = 0;
             if (kc > k && n >= kc) {
                 const double vl = (double)cand_dist[(size_t)q * kc + (kc - 1)];
-                if (vl - dv[k - 1] <= fmax(tie_eps, 4.0 * err32)) amb = 1;
+                if (vl - dk1 <= fmax(tie_eps, 4.0 * err32)) amb = 1;
             }
             ambiguous[q] = amb;
         }
@@ -274,10 +340,22 @@ extern "C" int mmmp_knn_refine(const double* ref64, const double* query64, int l
     if (metric->dim < 1 || metric->dim > ld64) return MMMP_ERR_ARG;
     if (n_query == 0) return MMMP_OK;
     const int group = metric->kind == MMMP_METRIC_L2 ? 1 : (metric->n_groups > 0 ? metric->dim / metric->n_groups : 1);
-    int g = mmmp_div_up(n_query, 128);
-    if (g > 148 * 8) g = 148 * 8;
-    MMMP_LAUNCH(knn_refine_kernel, g, 128, 0, stream, ref64, query64, ld64, metric->kind, metric->dim, group,
-                cand_idx, cand_dist, n_query, kc, k, tie_eps, out_idx, out_dist, ambiguous);
+    if (kc <= 32 && !getenv("MMMP_REFINE_SERIAL")) {
+        const int G = kc <= 16 ? 16 : 32;
+        int g = mmmp_div_up(n_query, 128 / G);
+        if (g > 148 * 32) g = 148 * 32;
+        if (G == 16)
+            MMMP_LAUNCH(knn_refine_group_kernel<16>, g, 128, 0, stream, ref64, query64, ld64, metric->kind, metric->dim,
+                        group, cand_idx, cand_dist, n_query, kc, k, tie_eps, out_idx, out_dist, ambiguous);
+        else
+            MMMP_LAUNCH(knn_refine_group_kernel<32>, g, 128, 0, stream, ref64, query64, ld64, metric->kind, metric->dim,
+                        group, cand_idx, cand_dist, n_query, kc, k, tie_eps, out_idx, out_dist, ambiguous);
+    } else {
+        int g = mmmp_div_up(n_query, 128);
+        if (g > 148 * 8) g = 148 * 8;
+        MMMP_LAUNCH(knn_refine_kernel, g, 128, 0, stream, ref64, query64, ld64, metric->kind, metric->dim, group,
+                    cand_idx, cand_dist, n_query, kc, k, tie_eps, out_idx, out_dist, ambiguous);
+    }
     MMMP_LAUNCH_CHECK();
     return MMMP_OK;
 }
