@@ -636,3 +636,32 @@ def test_ik_kernel_vs_float64_oracle(core, panda_model, cuda):
     far = np.tile([[3.0, 0.0, 0.5]], (5, 1))
     q, conv, res = w.ik(core.to_device_f64(far), None, core.to_device_f64(q0[:1]), 0, max_iters=50)
     assert not conv.cpu().numpy().any() and res.cpu().numpy()[:, 0].min() > 1.0
+
+
+def test_rerank_lanes_per_row_equals_the_sequential_rerank(core, cuda):
+    """mmmp_knn_refine ranks a row's candidates with one lane per candidate; rows with an exact float64
+    tie across rank k go through the sequential rule (the reference's bounded heap keeps the LARGER ids,
+    decoupled_prm.py:490-492).  Every output must equal the one-thread-per-row kernel's, on data made of
+    repeated points (ties everywhere), with empty candidate slots and with more than 16 candidates."""
+    import os
+    rng = np.random.default_rng(31)
+    base = np.round(rng.uniform(-1, 1, (500, 7)), 1)
+    q = base[rng.integers(0, 500, 4000)]                          # every point ~8 times: exact ties
+    feats = core.l2_features(core.to_device_f64(q))
+    for kc, k in ((12, 10), (12, 12), (26, 10), (16, 3)):
+        ci, cd = core.knn(feats, feats, kc, exclude_self=True)
+        ci[5, 7:] = -1                                             # a short row
+        ci[6, :] = -1                                              # an empty row
+        got = core.knn_refine(feats.x64, feats.x64, feats.m64, ci, cd, k)
+        os.environ["MMMP_REFINE_SERIAL"] = "1"
+        try:
+            want = core.knn_refine(feats.x64, feats.x64, feats.m64, ci, cd, k)
+        finally:
+            del os.environ["MMMP_REFINE_SERIAL"]
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), (kc, k)
+    # the data exercises the tie rule: float64 brute force on some rows, ties across rank 10
+    D = np.sqrt(((q[:200, None, :] - q[None, :, :]) ** 2).sum(-1))
+    D[np.arange(200), np.arange(200)] = np.inf
+    D.sort(1)
+    assert (D[:, 10] == D[:, 9]).sum() > 50
