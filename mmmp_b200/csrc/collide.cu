@@ -953,10 +953,12 @@ int pick_launch(K kernel, const mmmp_world* w, const SpatialArgs& A, int64_t wor
     // smaller CTAs keep more THREADS resident -- take the size with the most threads per SM
     block = 0;
     int per_sm = 1;
+    // the attribute belongs to the FUNCTION, not to the launch: always the device maximum, so that host
+    // threads launching for different worlds (or trying different CTA sizes) never lower it under each other
+    MMMP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     for (int b = 128; b >= 32; b >>= 1) {
         const size_t need = smem_bytes(w, A, b);
         if (need > (size_t)max_smem) continue;
-        MMMP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         int n = 0;
         MMMP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, b, need));
         if (n * b > per_sm * block) {
@@ -966,7 +968,6 @@ int pick_launch(K kernel, const mmmp_world* w, const SpatialArgs& A, int64_t wor
         }
     }
     if (block == 0) return MMMP_ERR_LIMIT;
-    MMMP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t want = (total_items + work_items_per_cta_hint - 1) / work_items_per_cta_hint;
     const int64_t resident = (int64_t)sms * per_sm;
     // persistent grid: a whole number of waves, never more CTAs than work

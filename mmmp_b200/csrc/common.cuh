@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 #include "../../include/mmmp_b200.h"
 
@@ -9,10 +11,18 @@
 #error "mmmp_b200 kernels are written for sm_100a (B200) only"
 #endif
 
+// MMMP_DEBUG=1 in the environment: the first failing CUDA call of an entry point is named on stderr
+static inline void mmmp_note_error(const char* file, int line, int code) {
+    if (getenv("MMMP_DEBUG")) fprintf(stderr, "mmmp_b200: CUDA error %d (%s) at %s:%d\n", code,
+                                      cudaGetErrorString((cudaError_t)code), file, line);
+}
 #define MMMP_CUDA_TRY(expr)                                            \
     do {                                                               \
         cudaError_t _e = (expr);                                       \
-        if (_e != cudaSuccess) return MMMP_ERR_CUDA_BASE + (int)_e;    \
+        if (_e != cudaSuccess) {                                       \
+            mmmp_note_error(__FILE__, __LINE__, (int)_e);              \
+            return MMMP_ERR_CUDA_BASE + (int)_e;                       \
+        }                                                              \
     } while (0)
 
 // every kernel launch of the library goes through this so that bench.py can
@@ -26,7 +36,10 @@ extern std::atomic<int64_t> g_mmmp_launches;
 #define MMMP_LAUNCH_CHECK()                                                        \
     do {                                                                           \
         cudaError_t _e = cudaPeekAtLastError();                                    \
-        if (_e != cudaSuccess) return MMMP_ERR_CUDA_BASE + (int)_e;                \
+        if (_e != cudaSuccess) {                                                   \
+            mmmp_note_error(__FILE__, __LINE__, (int)_e);                          \
+            return MMMP_ERR_CUDA_BASE + (int)_e;                                   \
+        }                                                                          \
     } while (0)
 
 // ---------------------------------------------------------------- device world

@@ -143,12 +143,20 @@ static int roadmap_host_impl(const mmmp_world* w, int robot, const double* q64_h
         DevBuf q64, q32, coll, idx, cnt, nq64, nq32, feat, filt, pos64, cidx, cdist, ridx, rdist, ecoll, amb, adj,
             deg, labels, ncomp;
         const int L = nj + 1;
-        auto T = [&](cudaError_t e) {
-            if (e != cudaSuccess && rc == MMMP_OK) rc = MMMP_ERR_CUDA_BASE + (int)e;
+        auto t_at = [&](cudaError_t e, int line) {
+            if (e != cudaSuccess && rc == MMMP_OK) {
+                mmmp_note_error(__FILE__, line, (int)e);
+                rc = MMMP_ERR_CUDA_BASE + (int)e;
+            }
         };
-        auto R = [&](int r) {
-            if (r != MMMP_OK && rc == MMMP_OK) rc = r;
+        auto r_at = [&](int r, int line) {
+            if (r != MMMP_OK && rc == MMMP_OK) {
+                mmmp_note_error(__FILE__, line, r >= MMMP_ERR_CUDA_BASE ? r - MMMP_ERR_CUDA_BASE : -r);
+                rc = r;
+            }
         };
+#define T(e) t_at((e), __LINE__)
+#define R(r) r_at((r), __LINE__)
         T(q64.alloc(sizeof(double) * N * D));
         T(q32.alloc(sizeof(float) * N * ld32));
         T(coll.alloc(N));
@@ -308,6 +316,9 @@ static int roadmap_host_impl(const mmmp_world* w, int robot, const double* q64_h
     cudaStreamDestroy(s);
     return rc;
 }
+
+#undef T
+#undef R
 
 extern "C" int mmmp_roadmap_candidates_host(const mmmp_world* w, int robot, const double* q64_h, int64_t N, int D,
                                             int metric_kind, int k, int n_steps, double step, uint32_t flags,

@@ -1024,7 +1024,13 @@ size_t scan_smem(int F4, int Q, int kc, int S) {
 template <int F4, int Q, bool DUAL = false>
 int launch_scan(const KnnArgs& A, int n_qblocks, void* stream) {
     const size_t smem = scan_smem(F4, Q, A.kc, A.S);
-    MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute belongs to the function: set to the device maximum, never to this launch's need -- two
+    // host threads searching with different candidate counts must not lower it under each other
+    int dev = 0, max_smem = 0;
+    MMMP_CUDA_TRY(cudaGetDevice(&dev));
+    MMMP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)max_smem) return MMMP_ERR_LIMIT;
+    MMMP_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel<F4, Q, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     dim3 grid(n_qblocks, A.n_splits, 1);
     MMMP_LAUNCH((knn_scan_kernel<F4, Q, DUAL>), grid, KNN_THREADS, smem, stream, A);
     MMMP_LAUNCH_CHECK();

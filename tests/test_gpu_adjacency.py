@@ -249,3 +249,34 @@ def test_candidate_table_verdicts_share_mutual_pairs(core, cuda):
     assert (plain == directed(rows, nbr, 50, 0.02)).all()
     assert (plain != want).sum() <= 5
     world.close()
+
+
+def test_roadmap_build_host_from_concurrent_threads(core, cuda):
+    """The host-buffer call creates its own streams and keeps no shared mutable state: two arms built
+    from two host threads at once (what bench.py's e2e does) return what the calls return one by one."""
+    from concurrent.futures import ThreadPoolExecutor
+    model = core.load_model("panda_spheres")
+    bases = [core.base_matrix((0.5, 0, 0.01), (0, 0, 1, 0)), core.base_matrix((-0.5, 0, 0.01))]
+    world = core.SpatialWorld([core.RobotSpec(model, b, 7 * i) for i, b in enumerate(bases)], [core.plane((0, 0, 1), 0.0)])
+    lim = np.array(model["joint_limits"])
+    rng = np.random.default_rng(8)
+    qs = [np.round(rng.uniform(lim[:, 0], lim[:, 1], (30_000, 7)), 2) for _ in range(2)]
+    keys = ("node_src", "nbr_idx", "nbr_dist", "edge_free", "adj", "deg", "labels")
+
+    dev_index = torch.cuda.current_device()
+
+    def call(a):
+        torch.cuda.set_device(dev_index)        # the current device is per host thread
+        r = world.roadmap_build_host(qs[a], a, core.METRIC_GROUP_L2_SUM, 10, 6, 50, 0.02)
+        return {k: np.array(r[k]) for k in keys} | {"n_nodes": r["n_nodes"], "n_components": r["n_components"]}
+
+    one_by_one = [call(0), call(1)]
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        for _ in range(3):
+            together = list(pool.map(call, range(2)))
+            for a in range(2):
+                assert together[a]["n_nodes"] == one_by_one[a]["n_nodes"] > 20_000
+                assert together[a]["n_components"] == one_by_one[a]["n_components"]
+                for k in keys:
+                    assert (together[a][k] == one_by_one[a][k]).all(), (a, k)
+    world.close()
