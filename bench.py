@@ -423,24 +423,17 @@ def run_ours(args):
     h2d = args.arms * args.nodes * 7 * 8
     d2h = args.arms * args.nodes * (4 + args.k * (4 + 8 + 1) + args.k2 * 4 + 4 + 4)
 
-    # The C-ABI call creates its own streams, so a caller with several arms on one GPU issues the calls
-    # from concurrent host threads: one arm's copies and latency-bound passes fill the gaps of another's
-    # kernels.  (The device-resident step above runs the arms back to back on one stream, so that its
-    # per-kernel event times stay clean for the roofline.)
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=len(teams.my_arms)) if team_size == 1 and len(teams.my_arms) > 1 else None
-
-    def e2e_arm(a):
-        torch.cuda.set_device(local_rank)       # the current device is per host thread
-        return world.roadmap_build_host(host_q[a].numpy(), a, core.METRIC_GROUP_L2_SUM, args.k, args.k2, 50, 0.02,
-                                        out=bufs[a])
-
+    # (Calling the arms of a rank from concurrent host threads is supported -- tests/test_gpu_adjacency.py --
+    # but measured no faster on average and far less repeatable: 156 ms in one run, 211 ms in the next, as
+    # four calls grow the stream-ordered pool against each other.  The arms are called one after the other.)
     def e2e_step():
-        if pool is not None:
-            return sum(int(r["n_nodes"]) for r in pool.map(e2e_arm, teams.my_arms))
         got = 0
         for a in teams.my_arms:
-            res = e2e_arm(a) if team_size == 1 else builders[a].build_host(host_q[a], args.k2, pinned_out=bufs[a])
+            if team_size == 1:
+                res = world.roadmap_build_host(host_q[a].numpy(), a, core.METRIC_GROUP_L2_SUM, args.k, args.k2, 50, 0.02,
+                                               out=bufs[a])
+            else:
+                res = builders[a].build_host(host_q[a], args.k2, pinned_out=bufs[a])
             got += int(res["n_nodes"])
         return got
 
@@ -560,7 +553,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te[0]) / args.steps,
                     "api": "mmmp_roadmap_build_host (C ABI, page-locked host buffers), one call per arm on the rank "
-                           "that owns the arm; the arms of a rank are called from concurrent host threads" if team_size == 1 else
+                           "that owns the arm" if team_size == 1 else
                            "RoadmapBuilder.build_host: the ranks of a team upload, check and return their row blocks"},
             "roofline": roofline,
             "algorithmic_speedup": algorithmic,
