@@ -346,6 +346,13 @@ int mmmp_pack_neighbour_records(const int32_t* rows_d, const int32_t* idx_d, con
 int mmmp_scatter_neighbour_records(const void* rec_d, int64_t n_records, int k, int64_t n,
                                    int32_t* idx_d, double* dist_d, uint8_t* amb_d, void* stream);
 
+/* The scan order of the neighbour search (host function, no device work): position
+ * of grid cell (x0, x1, x2), `bits` bits per axis, on the 3-D Hilbert curve the
+ * library sorts its rows along.  Consecutive positions are face-adjacent cells,
+ * which is what keeps a run of rows -- a tile, a query block -- compact
+ * (tests/test_abi_cpu.py checks the bijection and the adjacency).            */
+int mmmp_scan_order_cell(int x0, int x1, int x2, int bits, uint32_t* index_h);
+
 /* profiling aid: enable != 0 turns on five device counters of the scan kernel
  * (exact evaluations, list insertions, warp drains, tiles loaded, most tiles
  * loaded by one CTA); out5_h (may be NULL) receives and resets them;

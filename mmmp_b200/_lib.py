@@ -117,6 +117,7 @@ SIGNATURES = {
     "mmmp_pack_neighbour_records": [_P, _P, _P, _P, _I64, _I, _I64, _P, _P],
     "mmmp_scatter_neighbour_records": [_P, _I64, _I, _I64, _P, _P, _P, _P],
     "mmmp_knn_stats": [_I, _P],
+    "mmmp_scan_order_cell": [_I, _I, _I, _I, _P],
     "mmmp_edge_stats": [_I, _P],
     "mmmp_knn_refine": [_P, _P, _I, C.POINTER(Metric), _P, _P, _I64, _I, _I, _D, _P, _P, _P, _P],
     "mmmp_radius": [_P, _P, _I64, _P, _P, _I64, _I, _I, C.POINTER(Metric), C.POINTER(Metric), _D, _I, _I, _I, _I,

@@ -211,7 +211,7 @@ bbox_kernel(const float* __restrict__ rows, int ld, int nd, int64_t n, int* __re
     }
 }
 
-__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
     v = (v | (v << 16)) & 0x030000FFu;
     v = (v | (v << 8)) & 0x0300F00Fu;
     v = (v | (v << 4)) & 0x030C30C3u;
@@ -226,7 +226,7 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
 // transpose algorithm, AIP Conf. Proc. 707, 2004).  Consecutive cells of the curve share a face, so a
 // run of rows -- a tile, a CTA's query block -- never straddles one of the Z curve's jumps: the run's
 // bounding box stays close to the cells it covers.
-__device__ __forceinline__ uint32_t hilbert3(uint32_t x0, uint32_t x1, uint32_t x2, int bits) {
+__host__ __device__ __forceinline__ uint32_t hilbert3(uint32_t x0, uint32_t x1, uint32_t x2, int bits) {
     uint32_t X[3] = {x0, x1, x2};
     const uint32_t M = 1u << (bits - 1);
     for (uint32_t Q = M; Q > 1; Q >>= 1) {
@@ -1086,6 +1086,14 @@ int spatial_perm(const float* rows, int ld, int nd, int64_t n, const int* bbox_d
 }
 
 }  // namespace
+
+extern "C" int mmmp_scan_order_cell(int x0, int x1, int x2, int bits, uint32_t* index_h) {
+    if (!index_h || bits < 1 || bits > 10) return MMMP_ERR_ARG;
+    const int hi = 1 << bits;
+    if (x0 < 0 || x1 < 0 || x2 < 0 || x0 >= hi || x1 >= hi || x2 >= hi) return MMMP_ERR_ARG;
+    *index_h = hilbert3((uint32_t)x0, (uint32_t)x1, (uint32_t)x2, bits);
+    return MMMP_OK;
+}
 
 extern "C" int mmmp_knn_stats(int enable, unsigned long long* out5_h) {
     constexpr size_t bytes = 5 * sizeof(unsigned long long);

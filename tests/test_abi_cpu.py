@@ -68,6 +68,34 @@ def test_greedy_connect_matches_oracle(lib, golden):
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_scan_order_is_a_hilbert_curve(lib):
+    """The neighbour search sorts its rows by grid cell along mmmp_scan_order_cell (host function).
+    What the tile culling relies on: the numbering is a bijection of the grid and consecutive cells
+    share a face, so a run of consecutive rows never jumps across the grid."""
+    for bits in (1, 2, 3, 4):
+        n = 1 << bits
+        inv = np.full((n ** 3, 3), -1, np.int64)
+        out = C.c_uint32(0)
+        for x in range(n):
+            for y in range(n):
+                for z in range(n):
+                    assert lib.mmmp_scan_order_cell(x, y, z, bits, C.byref(out)) == 0
+                    assert out.value < n ** 3 and inv[out.value, 0] < 0, "not a bijection"
+                    inv[out.value] = (x, y, z)
+        steps = np.abs(np.diff(inv, axis=0)).sum(1)
+        assert (steps == 1).all(), f"bits={bits}: {int((steps != 1).sum())} steps between non-adjacent cells"
+    # spot checks on the 6-bit grid the 1 M-row search uses, and argument errors
+    rng = np.random.default_rng(0)
+    seen = set()
+    for x, y, z in rng.integers(0, 64, (2000, 3)):
+        assert lib.mmmp_scan_order_cell(int(x), int(y), int(z), 6, C.byref(out)) == 0
+        seen.add((out.value, (int(x), int(y), int(z))))
+    assert len({i for i, _ in seen}) == len({c for _, c in seen})
+    assert lib.mmmp_scan_order_cell(64, 0, 0, 6, C.byref(out)) != 0
+    assert lib.mmmp_scan_order_cell(0, 0, 0, 0, C.byref(out)) != 0
+    assert lib.mmmp_scan_order_cell(0, 0, 0, 3, None) != 0
+
+
 def test_no_cpu_fallback(lib):
     with pytest.raises(_lib.MmmpError):
         core.sample_uniform([0.0], [1.0], 4, seed=1)
