@@ -1,6 +1,6 @@
 """Parity of the path bench.py TIMES ("pin the path you benchmark").
 
-The neighbour scan takes its culled branch (Morton-sorted tiles, bounding-box culling, the
+The neighbour scan takes its culled branch (tiles sorted along the Hilbert curve, bounding-box culling, the
 fp32 centroid filter with its 2e-5 slack) only at >= 4096 references, so the golden vectors
 of tests/test_gpu_kernels.py (<= 3000 rows) never reach it.  Here the culled scan, the k + 2
 candidate pad, the fp64 re-rank and the re-search of ambiguous rows run at the BASELINE.json
