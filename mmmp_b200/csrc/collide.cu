@@ -1156,7 +1156,7 @@ __device__ __forceinline__ int find_in_row(const int32_t* __restrict__ row, int 
 
 // one thread per slot of rows [row_lo, row_hi): who evaluates the pair, in which direction
 __global__ void __launch_bounds__(256)
-knn_edges_classify_kernel(const int32_t* __restrict__ nbr, int k, int64_t row_lo, int64_t row_hi, int64_t win_lo,
+knn_edges_classify_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int64_t row_lo, int64_t row_hi, int64_t win_lo,
                           int64_t win_hi, int share, uint8_t* __restrict__ skip, int32_t* __restrict__ pair,
                           uint8_t* __restrict__ free_out) {
     const int64_t total = (row_hi - row_lo) * k;
@@ -1165,8 +1165,9 @@ knn_edges_classify_kernel(const int32_t* __restrict__ nbr, int k, int64_t row_lo
         const int32_t j = __ldg(nbr + row_lo * k + e);
         uint8_t code = SLOT_EVAL;
         int32_t a = (int32_t)i, b = j;
-        if (j < 0) {
+        if (j < 0 || j >= n) {   // an id outside the table is treated like an empty slot: blocked, never read
             code = SLOT_EMPTY;
+            b = -1;
         } else if (share && j != i && find_in_row(nbr + (int64_t)j * k, k, (int32_t)i) >= 0) {
             a = i < j ? (int32_t)i : j;    // mutual candidates: the reference's first check runs low -> high
             b = i < j ? j : (int32_t)i;
@@ -1271,7 +1272,7 @@ extern "C" int mmmp_collide_knn_edges(const mmmp_world* w, int robot, const void
     int32_t* edges = reinterpret_cast<int32_t*>(buf + off_edges);
     const int64_t win_lo = share_across_rows ? 0 : row_lo, win_hi = share_across_rows ? n : row_hi;
     int rc = MMMP_OK;
-    MMMP_LAUNCH(knn_edges_classify_kernel, slot_grid(total), 256, 0, stream, nbr_d, k, row_lo, row_hi, win_lo, win_hi,
+    MMMP_LAUNCH(knn_edges_classify_kernel, slot_grid(total), 256, 0, stream, nbr_d, n, k, row_lo, row_hi, win_lo, win_hi,
                 share, skip, pair, free_d);
     rc = mmmp_compact_free(skip, total, slots, count, stream);
     if (rc == MMMP_OK) {

@@ -203,7 +203,9 @@ def test_candidate_table_verdicts_share_mutual_pairs(core, cuda):
     feats = b.features(q64, q32)
     idx, _, _ = core.knn_exact(feats, feats, k)
     idx[17, 4] = -1                                       # an empty slot
+    idx[23, 0] = n + 5                                    # an id outside the table: treated like an empty slot
     nbr = _np(idx).astype(np.int64)
+    nbr[nbr >= n] = -1
     rows = np.repeat(np.arange(n), k).reshape(n, k)
     valid = nbr >= 0
     mutual = np.zeros((n, k), bool)
@@ -219,7 +221,7 @@ def test_candidate_table_verdicts_share_mutual_pairs(core, cuda):
     want = directed(a, c, 50, 0.02)
     assert 0.03 < 1.0 - want.mean() < 0.9
     got = _np(world.collide_knn_edges(q32, idx, 50, 0.02, 0, F))
-    assert (got == want).all() and got[17, 4] == 0
+    assert (got == want).all() and got[17, 4] == 0 and got[23, 0] == 0
     # both slots of a mutual pair agree by construction
     j = nbr[mutual]
     s_back = (nbr[j] == rows[mutual][:, None]).argmax(1)
