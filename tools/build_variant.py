@@ -5,7 +5,8 @@
 
 writes mmmp_b200/lib/variants/libmmmp_b200_NAME.so (git-ignored, travels with gpurun);
 select it at run time with MMMP_B200_LIB=<path>.
-Knobs: MMMP_KNN_{STAGES,TILE,RU,CWARPS,QSLACK,MINB,WALK,SPIN_NS} (csrc/knn_scan.cu),
+Knobs: MMMP_KNN_{STAGES,TILE,RU,RU2,RU4,CWARPS,QSLACK,MINB,MINB2,MINB4,WALK,SPIN_NS,PREFETCH,HILBERT}
+(csrc/knn_scan.cu; run-time: MMMP_KNN_BITS=<bits per axis of the sort grid>, MMMP_KNN_ORDER=1 heaviest-first launch),
 MMMP_EDGE_{LANES,DEFER_ROUNDS} (csrc/collide.cu); tools/knn_one.py prints a checksum of the answer
 so that variants can be compared for equality as well as for time.
 """
