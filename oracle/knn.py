@@ -6,6 +6,10 @@ heap_knn      : the bounded-heap loop of connect_nearest_neighbors_degree,
 greedy_degree : the accept pass decoupled_prm.py:496-503.
 distance_lists: connect_nearest_neighbors_distance candidate lists :556-563.
 brute_knn     : vectorised float64 ranking by (dist, id) for larger N.
+shared_verdict_table : the candidate-table verdicts of mmmp_collide_knn_edges restated -- a pair of nodes
+                that name each other is checked ONCE, from the lower id to the higher (the first of the
+                two is_collision_free_edge calls the accept pass :496-503 can make for it: nodes are
+                processed in id order); every other slot node -> candidate.
 """
 import heapq
 
@@ -83,3 +87,26 @@ def brute_knn(D, k, exclude_self=True):
         idx[i] = sel
         dist[i] = d[sel]
     return idx, dist
+
+
+def shared_verdict_table(idx, check):
+    """idx [n, k] candidate ids (-1 / out of range = empty slot); check(a, b) -> bool = is_collision_free_edge
+    walked from a to b (decoupled_prm.py:855-863).  -> (free [n, k] bool, calls): the verdict of every slot and
+    the list of directed checks actually made, one per distinct pair."""
+    idx = np.asarray(idx)
+    n, k = idx.shape
+    names = [set(int(j) for j in row if 0 <= j < n) for row in idx]
+    memo, calls = {}, []
+    free = np.zeros((n, k), bool)
+    for i in range(n):
+        for s in range(k):
+            j = int(idx[i, s])
+            if j < 0 or j >= n:
+                continue
+            mutual = j != i and i in names[j]
+            a, b = (min(i, j), max(i, j)) if mutual else (i, j)
+            if (a, b) not in memo:
+                memo[(a, b)] = bool(check(a, b))
+                calls.append((a, b))
+            free[i, s] = memo[(a, b)]
+    return free, calls

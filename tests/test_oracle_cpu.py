@@ -97,6 +97,44 @@ def test_heap_knn_and_greedy_match_reference(golden):
         assert np.abs(dist - ref_d).max() < 1e-9
 
 
+def test_shared_verdicts_build_the_reference_roadmap(golden):
+    """mmmp_collide_knn_edges checks a pair of mutual candidates once (low id -> high id).  Restated in
+    oracle.knn.shared_verdict_table and fed to the accept pass, it must build exactly the adjacency the
+    reference's production connect_nearest_neighbors_degree built on the golden samples (its edge rule is
+    the golden's; the reference loop asked for more checks than there are distinct pairs)."""
+    g = golden("panda_heap_knn")
+    qs = g["samples"]
+
+    def ef(a, b):                                              # tools/gen_golden.py ef(): the golden's edge rule
+        return (int(round((qs[a].sum() + qs[b].sum()) * 100)) % 7) != 0
+
+    for metric in ("fk", "l2"):
+        idx, dist = g[f"{metric}_knn_idx"], g[f"{metric}_knn_dist"]
+        free, calls = oknn.shared_verdict_table(idx, ef)
+        assert len(set(calls)) == len(calls)
+        pairs = {(min(i, int(j)), max(i, int(j))) for i in range(len(qs)) for j in idx[i]}
+        assert len({(min(a, b), max(a, b)) for a, b in calls}) == len(pairs) == len(calls)
+        mutual = sum(1 for i in range(len(qs)) for j in idx[i] if i in idx[int(j)])
+        assert 0.3 < mutual / idx.size < 0.95 and len(calls) == idx.size - mutual // 2
+        # every mutual pair is walked from its lower id: the first check of the reference's loop
+        assert all(a < b for a, b in calls if b in idx[a] and a in idx[b])
+        table = {(i, int(j)): bool(free[i, s]) for i in range(len(qs)) for s, j in enumerate(idx[i])}
+        cands = [[(dist[i, s], int(idx[i, s])) for s in range(idx.shape[1])] for i in range(len(qs))]
+        asked = []
+
+        def from_table(i, j):
+            asked.append((i, j))
+            return table[(i, j)]
+
+        adj = oknn.greedy_degree(cands, from_table, 6)
+        assert [len(a) for a in adj] == list(g[f"{metric}_degree_deg"])
+        assert sum(adj, []) == list(g[f"{metric}_degree_adj"])
+        # the reference's loop is lazy (it stops at k2 = 6 accepted edges) AND repeats itself: some pairs are
+        # asked for from both ends; the table holds one verdict for both
+        twice = len(asked) - len({(min(a, b), max(a, b)) for a, b in asked})
+        assert twice > 20 and len(asked) <= idx.size
+
+
 def test_scipy_fixture_knn(golden):
     # reference fixtures res/images/{random,halton}_{samples,degree_roadmap}.csv (k=5)
     g = golden("scipy_knn")
